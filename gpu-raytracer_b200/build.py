@@ -1,0 +1,75 @@
+"""Build recipes (explicit nvcc / g++ invocations, outputs in-tree so they travel with gpurun).
+
+  build_host()   -> gpu-raytracer_b200/host/libptb_host.so   C++ CPU BVH builder (SAH + CWBVH)
+  build_cuda()   -> gpu-raytracer_b200/csrc/libptb.so        sm_100a kernels + the C ABI of include/ptb.h
+  build_oracle() -> oracle/libpt_oracle.so                    CPU restatement (test infrastructure only)
+  build_ref()    -> oracle/_ref/*                             reference kernels compiled from /root/reference (if present)
+"""
+from __future__ import annotations
+
+import glob
+import os
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(PKG_DIR)
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _stale(out, srcs):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(s) > t for s in srcs if os.path.exists(s))
+
+
+def _run(cmd, cwd=None):
+    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: " + " ".join(cmd) + "\n" + r.stdout)
+    return r.stdout
+
+
+def build_host(force=False):
+    src = os.path.join(PKG_DIR, "host", "bvh_build.cpp")
+    out = os.path.join(PKG_DIR, "host", "libptb_host.so")
+    if force or _stale(out, [src]):
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", out, src])
+    return out
+
+
+def cuda_sources():
+    d = os.path.join(PKG_DIR, "csrc")
+    return sorted(glob.glob(os.path.join(d, "*.cu"))), sorted(glob.glob(os.path.join(d, "*.cuh")) + glob.glob(os.path.join(REPO_ROOT, "include", "*.h")))
+
+
+def build_cuda(force=False, verbose=False):
+    srcs, hdrs = cuda_sources()
+    out = os.path.join(PKG_DIR, "csrc", "libptb.so")
+    if force or _stale(out, srcs + hdrs):
+        cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC", "-shared",
+               "-I", os.path.join(REPO_ROOT, "include"), "-I", os.path.join(PKG_DIR, "csrc"), "-o", out, *srcs]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        log = _run(cmd)
+        if verbose:
+            print(log)
+    return out
+
+
+def build_oracle(force=False):
+    src = os.path.join(REPO_ROOT, "oracle", "pt_oracle.c")
+    out = os.path.join(REPO_ROOT, "oracle", "libpt_oracle.so")
+    if force or _stale(out, [src]):
+        _run(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-o", out, src, "-lm"])
+    return out
+
+
+def build_ref(force=False):
+    """Compile the reference's own kernels where they lie (needs /root/reference); no-op when absent."""
+    mk = os.path.join(REPO_ROOT, "oracle", "Makefile")
+    if not os.path.isdir("/root/reference/Src/CUDA") or not os.path.exists(mk):
+        return None
+    _run(["make", "-C", os.path.join(REPO_ROOT, "oracle"), "ref"] + (["-B"] if force else []))
+    return os.path.join(REPO_ROOT, "oracle", "_ref")

@@ -1,0 +1,491 @@
+// CPU BVH construction for the B200 wavefront path tracer (host side, no CUDA).
+//
+// The north star keeps BVH *build* on the CPU ("BVH build stays the reference's CPU path"),
+// so this file restates -- in our own code -- the three host algorithms whose OUTPUT FORMAT
+// the device traversal kernels consume, and which bench.py times as the CPU baseline:
+//
+//   * full-sweep SAH binary builder, one primitive per leaf
+//         (reference: Src/BVH/Builders/SAHBuilder.cpp:12-104, BVHPartitions.cpp:7-51,
+//          presort Src/Core/Sort.h:142-202)
+//   * SAH leaf collapser for the plain BVH2 variant (config 1)
+//         (reference: Src/BVH/BVHCollapser.cpp:14-114)
+//   * BVH2 -> 80-byte CWBVH (BVH8) conversion: 7-entry DP cost table, greedy octant
+//     slot assignment, quantised child boxes
+//         (reference: Src/BVH/Converters/BVH8Converter.cpp:7-335, node Src/BVH/BVH.h:61-80)
+//
+// Exposed through a small C ABI (ptbh_*) that the Python scene front-end drives via ctypes;
+// one call per mesh so the caller can fan the meshes out over a thread pool exactly like the
+// reference's AssetManager does (Src/Assets/AssetManager.cpp:57-95).
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+namespace {
+
+struct V3 { float x, y, z; };
+inline V3 vmin(V3 a, V3 b) { return { std::fmin(a.x, b.x), std::fmin(a.y, b.y), std::fmin(a.z, b.z) }; }
+inline V3 vmax(V3 a, V3 b) { return { std::fmax(a.x, b.x), std::fmax(a.y, b.y), std::fmax(a.z, b.z) }; }
+
+struct Box {
+    V3 lo, hi;
+    static Box empty() {
+        const float inf = std::numeric_limits<float>::infinity();
+        return { { inf, inf, inf }, { -inf, -inf, -inf } };
+    }
+    void grow(const Box& b) { lo = vmin(lo, b.lo); hi = vmax(hi, b.hi); }
+    void grow(V3 p) { lo = vmin(lo, p); hi = vmax(hi, p); }
+    bool is_empty() const { return lo.x == std::numeric_limits<float>::infinity(); }
+    // half surface area * 2, same operation order as the reference's AABB::surface_area
+    float area() const {
+        float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+        return 2.0f * (dx * dy + dy * dz + dz * dx);
+    }
+    V3 center() const { return { (lo.x + hi.x) * 0.5f, (lo.y + hi.y) * 0.5f, (lo.z + hi.z) * 0.5f }; }
+    // widen degenerate (flat) boxes, Src/Math/AABB.h fix_if_needed
+    void fatten(float epsilon = 0.001f) {
+        if (is_empty()) return;
+        float* mn = &lo.x; float* mx = &hi.x;
+        for (int d = 0; d < 3; d++) {
+            float eps = epsilon;
+            while (mx[d] - mn[d] < eps) { mn[d] -= eps; mx[d] += eps; eps *= 2.0f; }
+        }
+    }
+};
+
+// 32-byte binary node, bit-compatible with the device's BVH2 node (Src/BVH/BVH.h:11-23)
+struct Node2 {
+    Box      box;
+    int32_t  left_or_first;
+    uint32_t count_axis; // count : 30 (low bits), axis : 2 (high bits)
+    uint32_t count() const { return count_axis & 0x3fffffffu; }
+    uint32_t axis()  const { return count_axis >> 30; }
+    bool     leaf()  const { return count() > 0; }
+    void set(uint32_t count, uint32_t axis) { count_axis = (count & 0x3fffffffu) | (axis << 30); }
+};
+static_assert(sizeof(Node2) == 32, "BVH2 node must be 32 bytes");
+
+// 80-byte compressed wide node (Src/BVH/BVH.h:61-80)
+struct Node8 {
+    V3       p;
+    uint8_t  e[3];
+    uint8_t  imask;
+    uint32_t base_child;
+    uint32_t base_triangle;
+    uint8_t  meta[8];
+    uint8_t  qlo_x[8], qhi_x[8];
+    uint8_t  qlo_y[8], qhi_y[8];
+    uint8_t  qlo_z[8], qhi_z[8];
+};
+static_assert(sizeof(Node8) == 80, "CWBVH node must be 80 bytes");
+
+struct Prims {
+    std::vector<Box> box;
+    std::vector<V3>  center;
+};
+
+inline uint32_t float_sort_key(float f) {
+    uint32_t u; std::memcpy(&u, &f, 4);
+    uint32_t mask = uint32_t(-int32_t(u >> 31)) | 0x80000000u;
+    return u ^ mask;
+}
+
+// LSD radix sort of indices by float key, 4 passes of 8 bits (stable, like the reference's presort)
+void radix_sort_indices(std::vector<int>& idx, const std::vector<uint32_t>& key) {
+    size_t n = idx.size();
+    if (n <= 1) return;
+    std::vector<int> tmp(n);
+    int* in = idx.data(); int* out = tmp.data();
+    for (int pass = 0; pass < 4; pass++) {
+        uint32_t hist[256] = {};
+        int shift = pass * 8;
+        for (size_t i = 0; i < n; i++) hist[(key[in[i]] >> shift) & 255u]++;
+        uint32_t sum = 0;
+        for (int b = 0; b < 256; b++) { uint32_t c = hist[b]; hist[b] = sum; sum += c; }
+        for (size_t i = 0; i < n; i++) out[hist[(key[in[i]] >> shift) & 255u]++] = in[i];
+        std::swap(in, out);
+    }
+    // 4 passes -> result is back in idx
+}
+
+struct SAHBuilder {
+    const Prims& prims;
+    std::vector<Node2>& nodes;
+    std::vector<int> order[3];
+    std::vector<float> sweep;
+    std::vector<int>   scratch;
+    std::vector<uint8_t> goes_left;
+
+    SAHBuilder(const Prims& p, std::vector<Node2>& n) : prims(p), nodes(n) {}
+
+    struct Split { int index; int dim; float cost; Box left, right; };
+
+    Split find_split(int first, int count) {
+        Split s; s.index = -1; s.dim = -1; s.cost = std::numeric_limits<float>::infinity();
+        s.left = Box::empty(); s.right = Box::empty();
+        for (int dim = 0; dim < 3; dim++) {
+            const int* ord = order[dim].data();
+            Box l = Box::empty(), r = Box::empty();
+            for (int i = 1; i < count; i++) {
+                l.grow(prims.box[ord[first + i - 1]]);
+                sweep[i] = l.area() * float(i);
+            }
+            for (int i = count - 1; i > 0; i--) {
+                r.grow(prims.box[ord[first + i]]);
+                float cost = sweep[i] + r.area() * float(count - i);
+                if (cost <= s.cost) { s.cost = cost; s.index = first + i; s.dim = dim; s.right = r; }
+            }
+        }
+        const int* ord = order[s.dim].data();
+        for (int i = first; i < s.index; i++) s.left.grow(prims.box[ord[i]]);
+        return s;
+    }
+
+    void build_node(int node_index, int first, int count) {
+        if (count == 1) { // always split down to one primitive per leaf
+            nodes[node_index].left_or_first = first;
+            nodes[node_index].set(1, 0);
+            return;
+        }
+        Split s = find_split(first, count);
+        const int* ord = order[s.dim].data();
+        for (int i = first; i < s.index; i++)         goes_left[ord[i]] = 1;
+        for (int i = s.index; i < first + count; i++) goes_left[ord[i]] = 0;
+        for (int dim = 0; dim < 3; dim++) {
+            if (dim == s.dim) continue;
+            int l = 0, r = s.index - first;
+            int* o = order[dim].data();
+            for (int i = first; i < first + count; i++) {
+                int id = o[i];
+                if (goes_left[id]) scratch[l++] = id; else scratch[r++] = id;
+            }
+            std::memcpy(o + first, scratch.data(), size_t(count) * sizeof(int));
+        }
+        int left = int(nodes.size());
+        nodes[node_index].left_or_first = left;
+        nodes[node_index].set(0, uint32_t(s.dim));
+        nodes.emplace_back(); nodes.emplace_back();
+        nodes[left].box = s.left; nodes[left + 1].box = s.right;
+        int nl = s.index - first;
+        build_node(left, first, nl);
+        build_node(left + 1, first + nl, count - nl);
+    }
+
+    void build(std::vector<int>& indices_out) {
+        int n = int(prims.box.size());
+        nodes.clear(); nodes.reserve(size_t(2) * n + 2);
+        nodes.emplace_back(); nodes.emplace_back(); // root + dummy so siblings stay paired
+        Box root = Box::empty();
+        for (int i = 0; i < n; i++) root.grow(prims.box[i]);
+        nodes[0].box = root;
+        std::vector<uint32_t> key(n);
+        for (int dim = 0; dim < 3; dim++) {
+            order[dim].resize(n);
+            for (int i = 0; i < n; i++) {
+                order[dim][i] = i;
+                key[i] = float_sort_key((&prims.center[i].x)[dim]);
+            }
+            radix_sort_indices(order[dim], key);
+        }
+        sweep.resize(n + 1); scratch.resize(n); goes_left.assign(n, 0);
+        build_node(0, 0, n);
+        indices_out = order[0];
+    }
+};
+
+struct BVH2 { std::vector<Node2> nodes; std::vector<int> indices; };
+struct BVH8 { std::vector<Node8> nodes; std::vector<int> indices; };
+
+// ---------------------------------------------------------------- BVH2 leaf collapse
+struct Collapser {
+    const BVH2& in; BVH2& out; float c_node, c_leaf;
+    std::vector<uint8_t> merge;
+    struct Cost { int count; float sah; };
+
+    Cost cost(int ni) {
+        const Node2& n = in.nodes[ni];
+        if (n.leaf()) return { int(n.count()), float(n.count()) * c_leaf };
+        Cost l = cost(n.left_or_first), r = cost(n.left_or_first + 1);
+        int total = l.count + r.count;
+        float as_leaf = c_leaf * float(total);
+        float as_node = c_node + (in.nodes[n.left_or_first].box.area() * l.sah +
+                                  in.nodes[n.left_or_first + 1].box.area() * r.sah) / n.box.area();
+        if (as_leaf < as_node) { merge[ni] = 1; return { total, as_leaf }; }
+        return { total, as_node };
+    }
+    int gather(int ni) {
+        const Node2& n = in.nodes[ni];
+        if (n.leaf()) {
+            for (uint32_t i = 0; i < n.count(); i++) out.indices.push_back(in.indices[n.left_or_first + i]);
+            return int(n.count());
+        }
+        return gather(n.left_or_first) + gather(n.left_or_first + 1);
+    }
+    void emit(int dst, int src) {
+        const Node2 n = in.nodes[src];
+        out.nodes[dst].box = n.box;
+        out.nodes[dst].count_axis = n.count_axis;
+        if (n.leaf()) {
+            out.nodes[dst].left_or_first = int(out.indices.size());
+            for (uint32_t i = 0; i < n.count(); i++) out.indices.push_back(in.indices[n.left_or_first + i]);
+        } else if (merge[src]) {
+            int c = gather(src);
+            out.nodes[dst].set(uint32_t(c), n.axis());
+            out.nodes[dst].left_or_first = int(out.indices.size()) - c;
+        } else {
+            int l = int(out.nodes.size());
+            out.nodes[dst].left_or_first = l;
+            out.nodes.emplace_back(); out.nodes.emplace_back();
+            emit(l, n.left_or_first);
+            emit(l + 1, n.left_or_first + 1);
+        }
+    }
+    void run() {
+        merge.assign(in.nodes.size(), 0);
+        cost(0);
+        out.nodes.clear(); out.indices.clear();
+        out.nodes.reserve(in.nodes.size()); out.indices.reserve(in.indices.size());
+        out.nodes.emplace_back(); out.nodes.emplace_back();
+        emit(0, 0);
+    }
+};
+
+// ---------------------------------------------------------------- BVH2 -> CWBVH
+struct WideConverter {
+    const BVH2& in; BVH8& out;
+    enum Kind : int8_t { LEAF, INTERNAL, DISTRIBUTE };
+    struct Choice { Kind kind; int8_t dl, dr; float cost; };
+    std::vector<Choice> table; // 7 per BVH2 node: cost of representing the subtree with <= i+1 slots
+
+    WideConverter(const BVH2& i, BVH8& o) : in(i), out(o) {}
+    Choice& at(int node, int i) { return table[size_t(node) * 7 + i]; }
+
+    int fill_costs(int ni) {
+        const Node2& n = in.nodes[ni];
+        if (n.leaf()) {
+            float c = n.box.area() * float(n.count());
+            for (int i = 0; i < 7; i++) { at(ni, i).kind = LEAF; at(ni, i).cost = c; }
+            return int(n.count());
+        }
+        int L = n.left_or_first, R = L + 1;
+        int prims = fill_costs(L) + fill_costs(R);
+        const float inf = std::numeric_limits<float>::infinity();
+        { // whole subtree as ONE slot: either a (<=3 triangle) leaf or an internal node with 8 slots
+            float as_leaf = prims <= 3 ? float(prims) * n.box.area() : inf;
+            float best = inf; int8_t dl = -1, dr = -1;
+            for (int k = 0; k < 7; k++) {
+                float c = at(L, k).cost + at(R, 6 - k).cost;
+                if (c < best) { best = c; dl = int8_t(k); dr = int8_t(6 - k); }
+            }
+            float as_internal = best + n.box.area();
+            if (as_leaf < as_internal) { at(ni, 0).kind = LEAF; at(ni, 0).cost = as_leaf; }
+            else                        { at(ni, 0).kind = INTERNAL; at(ni, 0).cost = as_internal; }
+            at(ni, 0).dl = dl; at(ni, 0).dr = dr;
+        }
+        for (int i = 1; i < 7; i++) { // subtree spread over i+1 slots of the parent
+            float best = at(ni, i - 1).cost; int8_t dl = -1, dr = -1;
+            for (int k = 0; k < i; k++) {
+                float c = at(L, k).cost + at(R, i - k - 1).cost;
+                if (c < best) { best = c; dl = int8_t(k); dr = int8_t(i - k - 1); }
+            }
+            if (dl != -1) { at(ni, i).kind = DISTRIBUTE; at(ni, i).dl = dl; at(ni, i).dr = dr; at(ni, i).cost = best; }
+            else          { at(ni, i) = at(ni, i - 1); }
+        }
+        return prims;
+    }
+
+    void collect(int ni, int i, int kids[8], int& nk) {
+        const Node2& n = in.nodes[ni];
+        if (n.leaf()) { kids[nk++] = ni; return; }
+        int dl = at(ni, i).dl, dr = at(ni, i).dr;
+        int L = n.left_or_first, R = L + 1;
+        if (at(L, dl).kind == DISTRIBUTE) collect(L, dl, kids, nk); else kids[nk++] = L;
+        if (at(R, dr).kind == DISTRIBUTE) collect(R, dr, kids, nk); else kids[nk++] = R;
+    }
+
+    // greedy slot assignment: slot s is "best" for the child furthest along octant direction s
+    void assign_slots(int ni, int kids[8], int nk) {
+        V3 pc = in.nodes[ni].box.center();
+        float cost[8][8];
+        for (int c = 0; c < nk; c++) {
+            V3 cc = in.nodes[kids[c]].box.center();
+            V3 d = { cc.x - pc.x, cc.y - pc.y, cc.z - pc.z };
+            for (int s = 0; s < 8; s++) {
+                float sx = (s & 4) ? -1.0f : 1.0f, sy = (s & 2) ? -1.0f : 1.0f, sz = (s & 1) ? -1.0f : 1.0f;
+                cost[c][s] = d.x * sx + d.y * sy + d.z * sz;
+            }
+        }
+        int slot_of[8]; bool used[8] = {};
+        for (int c = 0; c < 8; c++) slot_of[c] = -1;
+        for (;;) {
+            float best = std::numeric_limits<float>::infinity(); int bs = -1, bc = -1;
+            for (int c = 0; c < nk; c++) if (slot_of[c] < 0)
+                for (int s = 0; s < 8; s++) if (!used[s] && cost[c][s] < best) { best = cost[c][s]; bs = s; bc = c; }
+            if (bs < 0) break;
+            used[bs] = true; slot_of[bc] = bs;
+        }
+        int copy[8];
+        for (int i = 0; i < 8; i++) { copy[i] = kids[i]; kids[i] = -1; }
+        for (int c = 0; c < nk; c++) kids[slot_of[c]] = copy[c];
+    }
+
+    int emit_leaf_prims(int ni) {
+        const Node2& n = in.nodes[ni];
+        if (n.leaf()) {
+            for (uint32_t i = 0; i < n.count(); i++) out.indices.push_back(in.indices[n.left_or_first + i]);
+            return int(n.count());
+        }
+        return emit_leaf_prims(n.left_or_first) + emit_leaf_prims(n.left_or_first + 1);
+    }
+
+    void emit(int dst, int src) {
+        Node8 node; std::memset(&node, 0, sizeof(node));
+        const Box& box = in.nodes[src].box;
+        node.p = box.lo;
+        const float denom = 1.0f / 255.0f;
+        float ex = exp2f(ceilf(log2f((box.hi.x - box.lo.x) * denom)));
+        float ey = exp2f(ceilf(log2f((box.hi.y - box.lo.y) * denom)));
+        float ez = exp2f(ceilf(log2f((box.hi.z - box.lo.z) * denom)));
+        float rx = 1.0f / ex, ry = 1.0f / ey, rz = 1.0f / ez;
+        uint32_t u;
+        std::memcpy(&u, &ex, 4); node.e[0] = uint8_t(u >> 23);
+        std::memcpy(&u, &ey, 4); node.e[1] = uint8_t(u >> 23);
+        std::memcpy(&u, &ez, 4); node.e[2] = uint8_t(u >> 23);
+
+        int kids[8] = { -1, -1, -1, -1, -1, -1, -1, -1 }; int nk = 0;
+        collect(src, 0, kids, nk);
+        assign_slots(src, kids, nk);
+
+        node.base_triangle = uint32_t(out.indices.size());
+        node.base_child    = uint32_t(out.nodes.size());
+        int n_internal = 0, n_tris = 0;
+        for (int i = 0; i < 8; i++) {
+            int k = kids[i];
+            if (k < 0) continue;
+            const Box& cb = in.nodes[k].box;
+            node.qlo_x[i] = uint8_t(floorf((cb.lo.x - node.p.x) * rx));
+            node.qlo_y[i] = uint8_t(floorf((cb.lo.y - node.p.y) * ry));
+            node.qlo_z[i] = uint8_t(floorf((cb.lo.z - node.p.z) * rz));
+            node.qhi_x[i] = uint8_t(ceilf((cb.hi.x - node.p.x) * rx));
+            node.qhi_y[i] = uint8_t(ceilf((cb.hi.y - node.p.y) * ry));
+            node.qhi_z[i] = uint8_t(ceilf((cb.hi.z - node.p.z) * rz));
+            if (at(k, 0).kind == LEAF) {
+                int t = emit_leaf_prims(k);
+                for (int j = 0; j < t; j++) node.meta[i] |= uint8_t(1u << (j + 5)); // unary count in top 3 bits
+                node.meta[i] |= uint8_t(n_tris);                                       // offset in low 5 bits
+                n_tris += t;
+            } else {
+                node.meta[i] = uint8_t((i + 24) | 0x20);
+                node.imask |= uint8_t(1u << i);
+                n_internal++;
+            }
+        }
+        for (int i = 0; i < n_internal; i++) out.nodes.emplace_back();
+        out.nodes[dst] = node;
+        int off = 0;
+        for (int i = 0; i < 8; i++) {
+            if (kids[i] < 0) continue;
+            if (node.imask & (1u << i)) emit(int(node.base_child) + off++, kids[i]);
+        }
+    }
+
+    void run() {
+        out.nodes.clear(); out.indices.clear();
+        out.indices.reserve(in.indices.size()); out.nodes.reserve(in.nodes.size());
+        out.nodes.emplace_back();
+        table.resize(in.nodes.size() * 7);
+        fill_costs(0);
+        emit(0, 0);
+    }
+};
+
+struct Built {
+    BVH2 bvh2;
+    BVH8 bvh8;
+    int  kind; // 2 or 8
+};
+
+void prims_from_triangles(const float* pos, int n, Prims& p) {
+    p.box.resize(n); p.center.resize(n);
+    for (int i = 0; i < n; i++) {
+        const float* t = pos + size_t(i) * 9;
+        V3 a = { t[0], t[1], t[2] }, b = { t[3], t[4], t[5] }, c = { t[6], t[7], t[8] };
+        Box bx = Box::empty(); bx.grow(a); bx.grow(b); bx.grow(c); bx.fatten();
+        p.box[i] = bx;
+        p.center[i] = { (a.x + b.x + c.x) / 3.0f, (a.y + b.y + c.y) / 3.0f, (a.z + b.z + c.z) / 3.0f };
+    }
+}
+
+Built* finish(Prims& prims, int kind, float sah_node, float sah_leaf) {
+    Built* b = new Built(); b->kind = kind;
+    BVH2 raw;
+    SAHBuilder(prims, raw.nodes).build(raw.indices);
+    if (kind == 8) {
+        WideConverter(raw, b->bvh8).run();
+    } else if (sah_leaf > 0.0f) {
+        Collapser c{ raw, b->bvh2, sah_node, sah_leaf, {} };
+        c.run();
+    } else {
+        b->bvh2 = std::move(raw);
+    }
+    return b;
+}
+
+} // namespace
+
+extern "C" {
+
+// Build over triangles: pos = n * 9 floats (v0,v1,v2). kind = 8 (CWBVH) or 2 (binary, SAH-collapsed leaves
+// when sah_leaf > 0; raw one-primitive leaves when sah_leaf <= 0).
+void* ptbh_build_triangles(const float* pos, int n, int kind, float sah_node, float sah_leaf) {
+    if (n <= 0 || (kind != 2 && kind != 8)) return nullptr;
+    Prims p; prims_from_triangles(pos, n, p);
+    return finish(p, kind, sah_node, sah_leaf);
+}
+
+// Build over already-boxed primitives (TLAS over instance boxes): aabb = n * 6 floats (min,max); centers = box centers.
+// TLAS BVH2 is never leaf-collapsed (reference: BVH2Converter is a plain copy, BVHConverter.h:17-26).
+void* ptbh_build_boxes(const float* aabb, int n, int kind) {
+    if (n <= 0 || (kind != 2 && kind != 8)) return nullptr;
+    Prims p; p.box.resize(n); p.center.resize(n);
+    for (int i = 0; i < n; i++) {
+        const float* a = aabb + size_t(i) * 6;
+        p.box[i] = { { a[0], a[1], a[2] }, { a[3], a[4], a[5] } };
+        p.center[i] = p.box[i].center();
+    }
+    return finish(p, kind, 0.0f, 0.0f);
+}
+
+int ptbh_kind(void* h)        { return static_cast<Built*>(h)->kind; }
+int ptbh_node_count(void* h)  { Built* b = static_cast<Built*>(h); return int(b->kind == 8 ? b->bvh8.nodes.size() : b->bvh2.nodes.size()); }
+int ptbh_index_count(void* h) { Built* b = static_cast<Built*>(h); return int(b->kind == 8 ? b->bvh8.indices.size() : b->bvh2.indices.size()); }
+int ptbh_node_bytes(void* h)  { return static_cast<Built*>(h)->kind == 8 ? 80 : 32; }
+
+// Copies nodes (80 or 32 bytes each) and primitive order out; adds the given offsets so the caller can
+// concatenate many BLAS into one node/triangle array (reference: Integrator.cpp:252-277 / 184-207).
+void ptbh_export(void* h, void* nodes_out, int* indices_out, int node_offset, int index_offset) {
+    Built* b = static_cast<Built*>(h);
+    if (b->kind == 8) {
+        Node8* dst = static_cast<Node8*>(nodes_out);
+        for (size_t i = 0; i < b->bvh8.nodes.size(); i++) {
+            dst[i] = b->bvh8.nodes[i];
+            dst[i].base_child    += uint32_t(node_offset);
+            dst[i].base_triangle += uint32_t(index_offset);
+        }
+        std::memcpy(indices_out, b->bvh8.indices.data(), b->bvh8.indices.size() * sizeof(int));
+    } else {
+        Node2* dst = static_cast<Node2*>(nodes_out);
+        for (size_t i = 0; i < b->bvh2.nodes.size(); i++) {
+            dst[i] = b->bvh2.nodes[i];
+            if (i == 1) continue; // dummy
+            if (dst[i].leaf()) dst[i].left_or_first += index_offset; else dst[i].left_or_first += node_offset;
+        }
+        std::memcpy(indices_out, b->bvh2.indices.data(), b->bvh2.indices.size() * sizeof(int));
+    }
+}
+
+void ptbh_free(void* h) { delete static_cast<Built*>(h); }
+
+} // extern "C"
