@@ -1,0 +1,590 @@
+// libptb.so -- host side of the B200 wavefront path tracer: device memory, uploads, the per-pass launch
+// sequence (the role of Pathtracer::render(), Src/Renderer/Integrators/Pathtracer.cpp:738-855) and the C ABI
+// declared in include/ptb.h.  CUDA runtime API + a little driver API for mip-mapped block-compressed textures.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ptb.h"
+#include "ptb_kernels.cuh"
+#include "ptb_post.cuh"
+
+#define CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx_fail(ctx, #expr, (int)e__); return (int)e__; } } while (0)
+#define CKD(expr) do { CUresult r__ = (expr); if (r__ != CUDA_SUCCESS) { ctx_fail(ctx, #expr, 1000 + (int)r__); return 1000 + (int)r__; } } while (0)
+
+// Driver-API entry points are resolved through the runtime (cudaGetDriverEntryPoint) so libptb.so carries no link-time
+// dependency on libcuda.so.1: the library still loads (and its symbol table can be checked) on a machine without a driver.
+struct DriverApi {
+    CUresult (*MipmappedArrayCreate)(CUmipmappedArray*, const CUDA_ARRAY3D_DESCRIPTOR*, unsigned) = nullptr;
+    CUresult (*MipmappedArrayGetLevel)(CUarray*, CUmipmappedArray, unsigned) = nullptr;
+    CUresult (*MipmappedArrayDestroy)(CUmipmappedArray) = nullptr;
+    CUresult (*Memcpy2D)(const CUDA_MEMCPY2D*) = nullptr;
+    CUresult (*TexObjectCreate)(CUtexObject*, const CUDA_RESOURCE_DESC*, const CUDA_TEXTURE_DESC*, const CUDA_RESOURCE_VIEW_DESC*) = nullptr;
+    CUresult (*TexObjectDestroy)(CUtexObject) = nullptr;
+    bool ok = false;
+};
+static DriverApi g_drv;
+static int load_driver_api() {
+    if (g_drv.ok) return 0;
+    struct { const char* name; void** slot; } want[] = {
+        { "cuMipmappedArrayCreate", (void**)&g_drv.MipmappedArrayCreate }, { "cuMipmappedArrayGetLevel", (void**)&g_drv.MipmappedArrayGetLevel },
+        { "cuMipmappedArrayDestroy", (void**)&g_drv.MipmappedArrayDestroy }, { "cuMemcpy2D", (void**)&g_drv.Memcpy2D },
+        { "cuTexObjectCreate", (void**)&g_drv.TexObjectCreate }, { "cuTexObjectDestroy", (void**)&g_drv.TexObjectDestroy } };
+    for (auto& w : want) {
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint(w.name, w.slot, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !*w.slot) { fprintf(stderr, "[ptb] driver entry point %s unavailable\n", w.name); return PTB_E_STATE; }
+    }
+    g_drv.ok = true;
+    return 0;
+}
+
+enum Stage { ST_GENERATE = 0, ST_TRACE, ST_SORT, ST_SHADE, ST_SHADOW, ST_POST, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = { "generate", "trace", "sort", "shade", "shadow_trace", "accumulate_or_svgf" };
+
+struct DeviceTexture {
+    CUmipmappedArray array = nullptr;
+    CUtexObject      tex = 0;
+};
+
+struct ptb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    Frame F;                         // host copy of the kernel parameter block
+    bool has_scene = false;
+    bool has_type[4] = { false, false, false, false };
+    bool has_lights = false;
+    int  mesh_capacity = 0, node_count = 0, bvh_kind = 8;
+    int  sm_count = 148;
+    int  owned_rows = 0;
+    std::vector<void*> allocs;       // everything cudaMalloc'ed, freed in ptb_destroy
+    std::vector<DeviceTexture> textures;
+    cudaArray_t sky_array = nullptr;
+    cudaArray_t lut_arrays[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    bool luts_ready = false;
+    uint4* tap_hits = nullptr;
+    long long launches = 0;
+    bool timing = false;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;
+    std::vector<cudaEvent_t> event_pool;
+    size_t event_used = 0;
+    float stage_ms[ST_COUNT] = {};
+    int last_sample_index = -1;
+    int frames_since_reset = 0;
+    std::string last_error;
+    float4* svgf_ping[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };
+};
+
+static void ctx_fail(ptb_ctx* ctx, const char* what, int code) {
+    if (!ctx) return;
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s failed with %d (%s)", what, code, code < 1000 ? cudaGetErrorString((cudaError_t)code) : "driver error");
+    ctx->last_error = buf;
+    fprintf(stderr, "[ptb] %s\n", buf);
+}
+
+template <typename T>
+static int dev_alloc(ptb_ctx* ctx, T** out, size_t count) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, (count ? count : 1) * sizeof(T)));
+    ctx->allocs.push_back(p);
+    *out = static_cast<T*>(p);
+    return 0;
+}
+template <typename T>
+static int dev_upload(ptb_ctx* ctx, const T** out, const void* src, size_t count) {
+    T* p = nullptr;
+    int e = dev_alloc(ctx, &p, count);
+    if (e) return e;
+    if (count) CK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = p;
+    return 0;
+}
+
+static int owned_rows_of(int height, int rank, int world, int band) {
+    int rows = 0;
+    for (int y = 0; y < height; y++) if ((y / band) % world == rank) rows++;
+    return rows;
+}
+
+static int grid_for(const ptb_ctx* ctx, int blocks_per_sm) { return ctx->sm_count * blocks_per_sm; }
+
+// ---------------------------------------------------------------------------------------------- lifetime
+extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int rank, int world, int band_rows) {
+    if (!out || width <= 0 || height <= 0 || world <= 0 || rank < 0 || rank >= world || band_rows <= 0) return PTB_E_BADARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { fprintf(stderr, "[ptb] no CUDA device: the product path has no CPU fallback\n"); return e != cudaSuccess ? (int)e : (int)cudaErrorNoDevice; }
+    if (device < 0 || device >= n) return PTB_E_BADARG;
+    ptb_ctx* ctx = new (std::nothrow) ptb_ctx();
+    if (!ctx) return PTB_E_STATE;
+    ctx->device = device;
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+
+    Frame& F = ctx->F;
+    memset(&F, 0, sizeof(F));
+    F.width = width; F.height = height; F.pitch = (width + 31) / 32 * 32;
+    F.rank = rank; F.world = world; F.band_rows = band_rows;
+    ctx->owned_rows = owned_rows_of(height, rank, world, band_rows);
+    F.local_pixels = ctx->owned_rows * width;
+
+    // defaults of GPUConfig (Common.h:39-67)
+    F.config.reconstruction_filter = 2; F.config.aov_mask = 1u; F.config.num_bounces = 10;
+    F.config.enable_mipmapping = 1; F.config.enable_next_event_estimation = 1; F.config.enable_multiple_importance_sampling = 1;
+    F.config.enable_russian_roulette = 1; F.config.enable_svgf = 0; F.config.enable_spatial_variance = 1; F.config.enable_taa = 1;
+    F.config.alpha_colour = 0.1f; F.config.alpha_moment = 0.1f; F.config.num_atrous_iterations = 6;
+    F.config.sigma_z = 4.0f; F.config.sigma_n = 16.0f; F.config.sigma_l = 10.0f;
+
+    const size_t N = (size_t)F.local_pixels;
+    for (int i = 0; i < 2; i++) {
+        if (dev_alloc(ctx, &F.q[i].od0, N) || dev_alloc(ctx, &F.q[i].od1, N) || dev_alloc(ctx, &F.q[i].hit, N) ||
+            dev_alloc(ctx, &F.q[i].path, N) || dev_alloc(ctx, &F.q[i].pix, N) || dev_alloc(ctx, &F.q[i].medium, N)) { ptb_destroy(ctx); return PTB_E_STATE; }
+    }
+    if (dev_alloc(ctx, &F.sq.od0, N) || dev_alloc(ctx, &F.sq.od1, N) || dev_alloc(ctx, &F.sq.illum, N)) { ptb_destroy(ctx); return PTB_E_STATE; }
+    for (int m = 0; m < 4; m++) if (dev_alloc(ctx, &F.matq[m], N)) { ptb_destroy(ctx); return PTB_E_STATE; }
+    if (dev_alloc(ctx, &F.counters, 1) || dev_alloc(ctx, &F.totals, 1)) { ptb_destroy(ctx); return PTB_E_STATE; }
+    CK(cudaMemsetAsync(F.counters, 0, sizeof(Counters), ctx->stream));
+    CK(cudaMemsetAsync(F.totals, 0, sizeof(RayTotals), ctx->stream));
+    const size_t pixels = (size_t)F.pitch * F.height;
+    if (dev_alloc(ctx, &F.display, pixels) || dev_alloc(ctx, &ctx->tap_hits, pixels)) { ptb_destroy(ctx); return PTB_E_STATE; }
+    CK(cudaMemsetAsync(F.display, 0, pixels * sizeof(float4), ctx->stream));
+    // RADIANCE is always on (Pathtracer.cpp:267-268)
+    if (dev_alloc(ctx, &F.aov[PTB_AOV_RADIANCE].fb, pixels) || dev_alloc(ctx, &F.aov[PTB_AOV_RADIANCE].acc, pixels)) { ptb_destroy(ctx); return PTB_E_STATE; }
+    CK(cudaMemsetAsync(F.aov[PTB_AOV_RADIANCE].fb, 0, pixels * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(F.aov[PTB_AOV_RADIANCE].acc, 0, pixels * sizeof(float4), ctx->stream));
+
+    CK(cudaFuncSetAttribute(k_trace8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_trace8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void ptb_destroy(ptb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (g_drv.ok) for (auto& t : ctx->textures) { if (t.tex) g_drv.TexObjectDestroy(t.tex); if (t.array) g_drv.MipmappedArrayDestroy(t.array); }
+    if (ctx->F.sky_tex) cudaDestroyTextureObject(ctx->F.sky_tex);
+    if (ctx->sky_array) cudaFreeArray(ctx->sky_array);
+    cudaTextureObject_t luts[6] = { ctx->F.lut_dielectric_dir_enter, ctx->F.lut_dielectric_dir_leave, ctx->F.lut_dielectric_enter,
+                                    ctx->F.lut_dielectric_leave, ctx->F.lut_conductor_dir, ctx->F.lut_conductor };
+    for (int i = 0; i < 6; i++) { if (luts[i]) cudaDestroyTextureObject(luts[i]); if (ctx->lut_arrays[i]) cudaFreeArray(ctx->lut_arrays[i]); }
+    for (void* p : ctx->allocs) cudaFree(p);
+    for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+// ---------------------------------------------------------------------------------------------- AOV management
+static int ensure_aov(ptb_ctx* ctx, int k) {
+    Frame& F = ctx->F;
+    if (F.aov[k].fb) return 0;
+    const size_t pixels = (size_t)F.pitch * F.height;
+    int e = dev_alloc(ctx, &F.aov[k].fb, pixels); if (e) return e;
+    e = dev_alloc(ctx, &F.aov[k].acc, pixels); if (e) return e;
+    CK(cudaMemsetAsync(F.aov[k].fb, 0, pixels * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(F.aov[k].acc, 0, pixels * sizeof(float4), ctx->stream));
+    return 0;
+}
+
+static int ensure_svgf(ptb_ctx* ctx) {
+    Frame& F = ctx->F;
+    if (F.svgf.history_length) return 0;
+    const size_t pixels = (size_t)F.pitch * F.height;
+    int e = 0;
+    e |= dev_alloc(ctx, &F.svgf.gbuf_normal_depth, pixels); e |= dev_alloc(ctx, &F.svgf.gbuf_ids, pixels); e |= dev_alloc(ctx, &F.svgf.gbuf_screen_prev, pixels);
+    e |= dev_alloc(ctx, &F.svgf.moment, pixels); e |= dev_alloc(ctx, &F.svgf.history_length, pixels);
+    e |= dev_alloc(ctx, &F.svgf.history_direct, pixels); e |= dev_alloc(ctx, &F.svgf.history_indirect, pixels);
+    e |= dev_alloc(ctx, &F.svgf.history_moment, pixels); e |= dev_alloc(ctx, &F.svgf.history_normal_depth, pixels);
+    e |= dev_alloc(ctx, &F.svgf.taa_prev, pixels); e |= dev_alloc(ctx, &F.svgf.taa_curr, pixels);
+    if (e) return PTB_E_STATE;
+    CK(cudaMemsetAsync(F.svgf.gbuf_normal_depth, 0, pixels * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(F.svgf.gbuf_ids, 0, pixels * sizeof(int2), ctx->stream));
+    CK(cudaMemsetAsync(F.svgf.gbuf_screen_prev, 0, pixels * sizeof(float2), ctx->stream));
+    CK(cudaMemsetAsync(F.svgf.moment, 0, pixels * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(F.svgf.history_length, 0, pixels * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(F.svgf.history_direct, 0, pixels * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(F.svgf.history_indirect, 0, pixels * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(F.svgf.history_moment, 0, pixels * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(F.svgf.history_normal_depth, 0, pixels * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(F.svgf.taa_prev, 0, pixels * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(F.svgf.taa_curr, 0, pixels * sizeof(float4), ctx->stream));
+    return 0;
+}
+
+extern "C" int ptb_set_config(ptb_ctx* ctx, const ptb_config* config) {
+    if (!ctx || !config) return PTB_E_BADARG;
+    if (config->num_bounces < 1 || config->num_bounces > PTB_MAX_BOUNCES - 1) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    ctx->F.config = *config;
+    ctx->F.config.aov_mask |= 1u;
+    if (config->enable_svgf) {   // svgf_init enables DIRECT / INDIRECT / ALBEDO (Pathtracer.cpp:331-333)
+        ctx->F.config.aov_mask |= (1u << PTB_AOV_RADIANCE_DIRECT) | (1u << PTB_AOV_RADIANCE_INDIRECT) | (1u << PTB_AOV_ALBEDO);
+        int e = ensure_svgf(ctx); if (e) return e;
+    }
+    for (int k = 0; k < PTB_AOV_COUNT; k++) if (ctx->F.config.aov_mask & (1u << k)) { int e = ensure_aov(ctx, k); if (e) return e; }
+    ctx->frames_since_reset = 0;
+    return 0;
+}
+
+extern "C" int ptb_set_camera(ptb_ctx* ctx, const ptb_camera* camera, const float* vp, const float* vp_prev) {
+    if (!ctx || !camera) return PTB_E_BADARG;
+    ctx->F.camera = *camera;
+    if (vp) memcpy(ctx->F.svgf.view_projection, vp, 64);
+    if (vp_prev) memcpy(ctx->F.svgf.view_projection_prev, vp_prev, 64);
+    else if (vp) memcpy(ctx->F.svgf.view_projection_prev, vp, 64);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- textures
+static int create_texture(ptb_ctx* ctx, const ptb_texture& t, DeviceTexture& out) {
+    // Same object the reference builds (Integrator.cpp:42-94): mip-mapped array, wrap addressing, trilinear,
+    // anisotropic; BC1 = 2 x uint32 per 4x4 block viewed through a BC1 resource view.
+    const bool bc1 = t.format == 1;
+    const int aw = bc1 ? (t.width + 3) / 4 : t.width, ah = bc1 ? (t.height + 3) / 4 : t.height;
+    CUDA_ARRAY3D_DESCRIPTOR ad; memset(&ad, 0, sizeof(ad));
+    ad.Width = aw; ad.Height = ah; ad.Depth = 0;
+    ad.NumChannels = bc1 ? 2 : 4;
+    ad.Format = bc1 ? CU_AD_FORMAT_UNSIGNED_INT32 : CU_AD_FORMAT_UNSIGNED_INT8;
+    CKD(g_drv.MipmappedArrayCreate(&out.array, &ad, t.num_levels));
+    for (int l = 0; l < t.num_levels; l++) {
+        CUarray level;
+        CKD(g_drv.MipmappedArrayGetLevel(&level, out.array, l));
+        int lw = aw >> l; if (lw < 1) lw = 1;
+        int lh = ah >> l; if (lh < 1) lh = 1;
+        CUDA_MEMCPY2D cp; memset(&cp, 0, sizeof(cp));
+        cp.srcMemoryType = CU_MEMORYTYPE_HOST; cp.srcHost = t.levels[l];
+        cp.srcPitch = (size_t)lw * (bc1 ? 8 : 4);
+        cp.dstMemoryType = CU_MEMORYTYPE_ARRAY; cp.dstArray = level;
+        cp.WidthInBytes = cp.srcPitch; cp.Height = lh;
+        CKD(g_drv.Memcpy2D(&cp));
+    }
+    CUDA_RESOURCE_DESC rd; memset(&rd, 0, sizeof(rd));
+    rd.resType = CU_RESOURCE_TYPE_MIPMAPPED_ARRAY; rd.res.mipmap.hMipmappedArray = out.array;
+    CUDA_TEXTURE_DESC td; memset(&td, 0, sizeof(td));
+    td.addressMode[0] = CU_TR_ADDRESS_MODE_WRAP; td.addressMode[1] = CU_TR_ADDRESS_MODE_WRAP; td.addressMode[2] = CU_TR_ADDRESS_MODE_CLAMP;
+    td.filterMode = CU_TR_FILTER_MODE_LINEAR; td.mipmapFilterMode = CU_TR_FILTER_MODE_LINEAR;
+    td.mipmapLevelBias = 0.0f; td.maxAnisotropy = 16;   // the reference queries GL_MAX_TEXTURE_MAX_ANISOTROPY_EXT (16 on NVIDIA)
+    td.minMipmapLevelClamp = 0.0f; td.maxMipmapLevelClamp = float(t.num_levels - 1);
+    td.flags = CU_TRSF_NORMALIZED_COORDINATES;
+    CUDA_RESOURCE_VIEW_DESC vd; memset(&vd, 0, sizeof(vd));
+    vd.format = bc1 ? CU_RES_VIEW_FORMAT_UNSIGNED_BC1 : CU_RES_VIEW_FORMAT_UINT_4X8;
+    vd.width = bc1 ? (size_t)aw * 4 : aw; vd.height = bc1 ? (size_t)ah * 4 : ah;
+    vd.firstMipmapLevel = 0; vd.lastMipmapLevel = t.num_levels - 1;
+    CKD(g_drv.TexObjectCreate(&out.tex, &rd, &td, &vd));
+    return 0;
+}
+
+static int create_float_texture(ptb_ctx* ctx, cudaArray_t* arr, cudaTextureObject_t* tex, const float* host, int channels,
+                                int w, int h, int d, bool device_src) {
+    cudaChannelFormatDesc cd = channels == 4 ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<float>();
+    if (d > 0) CK(cudaMalloc3DArray(arr, &cd, make_cudaExtent(w, h, d)));
+    else       CK(cudaMallocArray(arr, &cd, w, h));
+    size_t texel = sizeof(float) * channels;
+    cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (d > 0) {
+        cudaMemcpy3DParms p; memset(&p, 0, sizeof(p));
+        p.srcPtr = make_cudaPitchedPtr(const_cast<float*>(host), w * texel, w, h);
+        p.dstArray = *arr; p.extent = make_cudaExtent(w, h, d); p.kind = kind;
+        CK(cudaMemcpy3D(&p));
+    } else {
+        CK(cudaMemcpy2DToArray(*arr, 0, 0, host, w * texel, w * texel, h > 0 ? h : 1, kind));
+    }
+    cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray; rd.res.array.array = *arr;
+    cudaTextureDesc td; memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 1;
+    CK(cudaCreateTextureObject(tex, &rd, &td, nullptr));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- Kulla-Conty LUT bake
+static int bake_luts(ptb_ctx* ctx) {
+    if (ctx->luts_ready) return 0;
+    Frame& F = ctx->F;
+    const int D = PTB_LUT_DIELECTRIC_DIM, C = PTB_LUT_CONDUCTOR_DIM;
+    float *dir = nullptr, *avg = nullptr;
+    CK(cudaMalloc(&dir, sizeof(float) * D * D * D));
+    CK(cudaMalloc(&avg, sizeof(float) * D * D));
+    cudaTextureObject_t* dir_tex[2] = { &F.lut_dielectric_dir_enter, &F.lut_dielectric_dir_leave };
+    cudaTextureObject_t* avg_tex[2] = { &F.lut_dielectric_enter, &F.lut_dielectric_leave };
+    for (int pass = 0; pass < 2; pass++) {
+        bool entering = pass == 0;
+        k_integrate_dielectric<<<(D * D * D + 255) / 256, 256, 0, ctx->stream>>>(F, entering, dir);
+        k_average_dielectric<<<(D * D + 255) / 256, 256, 0, ctx->stream>>>(dir, avg);
+        ctx->launches += 2;
+        CK(cudaStreamSynchronize(ctx->stream));
+        int e = create_float_texture(ctx, &ctx->lut_arrays[pass], dir_tex[pass], dir, 1, D, D, D, true); if (e) return e;
+        e = create_float_texture(ctx, &ctx->lut_arrays[2 + pass], avg_tex[pass], avg, 1, D, D, 0, true); if (e) return e;
+    }
+    float *cdir = nullptr, *cavg = nullptr;
+    CK(cudaMalloc(&cdir, sizeof(float) * C * C));
+    CK(cudaMalloc(&cavg, sizeof(float) * C));
+    k_integrate_conductor<<<(C * C + 255) / 256, 256, 0, ctx->stream>>>(F, cdir);
+    k_average_conductor<<<1, 256, 0, ctx->stream>>>(cdir, cavg);
+    ctx->launches += 2;
+    CK(cudaStreamSynchronize(ctx->stream));
+    int e = create_float_texture(ctx, &ctx->lut_arrays[4], &F.lut_conductor_dir, cdir, 1, C, C, 0, true); if (e) return e;
+    e = create_float_texture(ctx, &ctx->lut_arrays[5], &F.lut_conductor, cavg, 1, C, 0, 0, true); if (e) return e;
+    cudaFree(dir); cudaFree(avg); cudaFree(cdir); cudaFree(cavg);
+    ctx->luts_ready = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- scene upload
+extern "C" int ptb_upload_scene(ptb_ctx* ctx, const ptb_scene* s) {
+    if (!ctx || !s) return PTB_E_BADARG;
+    if (ctx->has_scene) return PTB_E_STATE;     // one scene per ctx (create a new ctx to switch scenes)
+    if (!s->triangles || !s->bvh_nodes || s->mesh_count <= 0 || (s->bvh_kind != 8 && s->bvh_kind != 2) || !s->pmj_samples || !s->blue_noise || !s->sky)
+        return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    { int de = load_driver_api(); if (de) return de; }
+    Frame& F = ctx->F;
+    int e = 0;
+    e |= dev_upload<float4>(ctx, &F.triangles, s->triangles, (size_t)s->triangle_count * 6);
+    ctx->bvh_kind = s->bvh_kind; ctx->node_count = s->bvh_node_count;
+    if (s->bvh_kind == 8) e |= dev_upload<float4>(ctx, &F.nodes8, s->bvh_nodes, (size_t)s->bvh_node_count * 5);
+    else                  e |= dev_upload<float4>(ctx, &F.nodes2, s->bvh_nodes, (size_t)s->bvh_node_count * 2);
+    F.tlas_nodes = s->bvh_kind == 8 ? s->tlas_node_count : 0;
+    ctx->mesh_capacity = s->mesh_count;
+    e |= dev_upload<int>(ctx, &F.mesh_roots, s->mesh_bvh_root_indices, s->mesh_count);
+    e |= dev_upload<int>(ctx, &F.mesh_material_ids, s->mesh_material_ids, s->mesh_count);
+    e |= dev_upload<float4>(ctx, &F.mesh_transforms, s->mesh_transforms, (size_t)s->mesh_count * 3);
+    e |= dev_upload<float4>(ctx, &F.mesh_transforms_inv, s->mesh_transforms_inv, (size_t)s->mesh_count * 3);
+    e |= dev_upload<float4>(ctx, &F.mesh_transforms_prev, s->mesh_transforms_prev ? s->mesh_transforms_prev : s->mesh_transforms, (size_t)s->mesh_count * 3);
+    e |= dev_upload<signed char>(ctx, &F.material_types, s->material_types, s->material_count);
+    e |= dev_upload<float4>(ctx, &F.materials, s->materials, (size_t)s->material_count * 2);
+    e |= dev_upload<float4>(ctx, &F.media, s->media, (size_t)(s->medium_count > 0 ? s->medium_count : 0) * 2);
+    e |= dev_upload<float2>(ctx, &F.pmj, s->pmj_samples, (size_t)PTB_PMJ_SEQUENCES * PTB_PMJ_SAMPLES);
+    e |= dev_upload<uchar2>(ctx, &F.blue_noise, s->blue_noise, (size_t)PTB_BLUE_NOISE_TEXTURES * PTB_BLUE_NOISE_DIM * PTB_BLUE_NOISE_DIM);
+    if (e) return PTB_E_STATE;
+
+    // which shade kernels run: scene.has_<type> is over ALL materials (Scene::check_materials, Scene.cpp)
+    for (int i = 0; i < s->material_count; i++) {
+        int t = s->material_types[i];
+        if (t >= PTB_MAT_DIFFUSE && t <= PTB_MAT_CONDUCTOR) ctx->has_type[t - PTB_MAT_DIFFUSE] = true;
+    }
+    // lights
+    F.lights_total_weight = s->light_mesh_count > 0 ? s->lights_total_weight : 0.0f;
+    ctx->has_lights = s->light_mesh_count > 0 && s->lights_total_weight > 0.0f;
+    F.light_mesh_count = s->light_mesh_count;
+    e |= dev_upload<int>(ctx, &F.light_triangle_indices, s->light_triangle_indices, s->light_triangle_count);
+    e |= dev_upload<float>(ctx, &F.light_triangle_cdf, s->light_triangle_cumulative_probability, s->light_triangle_count);
+    e |= dev_upload<float>(ctx, &F.light_mesh_cdf, s->light_mesh_cumulative_probability, s->light_mesh_count);
+    e |= dev_upload<int2>(ctx, &F.light_mesh_triangle_span, s->light_mesh_triangle_span, s->light_mesh_count);
+    e |= dev_upload<int>(ctx, &F.light_mesh_transform_indices, s->light_mesh_transform_indices, s->light_mesh_count);
+    if (e) return PTB_E_STATE;
+
+    // textures
+    std::vector<TextureEntry> table((size_t)(s->texture_count > 0 ? s->texture_count : 0));
+    ctx->textures.resize(table.size());
+    for (size_t i = 0; i < table.size(); i++) {
+        int te = create_texture(ctx, s->textures[i], ctx->textures[i]); if (te) return te;
+        table[i].tex = (cudaTextureObject_t)ctx->textures[i].tex; table[i].lod_bias = s->textures[i].lod_bias; table[i].pad = 0.0f;
+    }
+    e |= dev_upload<TextureEntry>(ctx, &F.textures, table.data(), table.size());
+    CK(cudaStreamSynchronize(ctx->stream));   // `table` is a host temporary
+
+    // sky: float4 array, bilinear, clamp (Integrator.cpp:285-296)
+    e = create_float_texture(ctx, &ctx->sky_array, &F.sky_tex, s->sky, 4, s->sky_width, s->sky_height, 0, false); if (e) return e;
+    F.sky_scale = s->sky_scale;
+
+    ctx->has_scene = true;
+    if (ctx->has_type[2] || ctx->has_type[3]) { e = bake_luts(ctx); if (e) return e; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int ptb_update_instances(ptb_ctx* ctx, const void* tlas_nodes, int tlas_node_count, int mesh_count,
+                                    const int32_t* roots, const int32_t* material_ids, const float* xf, const float* xf_inv, const float* xf_prev) {
+    if (!ctx || !ctx->has_scene) return PTB_E_NOSCENE;
+    if (mesh_count != ctx->mesh_capacity || tlas_node_count > 2 * mesh_count || !tlas_nodes) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    Frame& F = ctx->F;
+    size_t node_bytes = ctx->bvh_kind == 8 ? 80 : 32;
+    void* dst = ctx->bvh_kind == 8 ? (void*)F.nodes8 : (void*)F.nodes2;
+    CK(cudaMemcpyAsync(dst, tlas_nodes, node_bytes * tlas_node_count, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->bvh_kind == 8) F.tlas_nodes = tlas_node_count;
+    if (roots) CK(cudaMemcpyAsync((void*)F.mesh_roots, roots, sizeof(int) * mesh_count, cudaMemcpyHostToDevice, ctx->stream));
+    if (material_ids) CK(cudaMemcpyAsync((void*)F.mesh_material_ids, material_ids, sizeof(int) * mesh_count, cudaMemcpyHostToDevice, ctx->stream));
+    if (xf) CK(cudaMemcpyAsync((void*)F.mesh_transforms, xf, 48 * (size_t)mesh_count, cudaMemcpyHostToDevice, ctx->stream));
+    if (xf_inv) CK(cudaMemcpyAsync((void*)F.mesh_transforms_inv, xf_inv, 48 * (size_t)mesh_count, cudaMemcpyHostToDevice, ctx->stream));
+    if (xf_prev) CK(cudaMemcpyAsync((void*)F.mesh_transforms_prev, xf_prev, 48 * (size_t)mesh_count, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- render
+struct StageTimer {
+    ptb_ctx* ctx; int stage; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t take(ptb_ctx* c) {
+        if (c->event_used == c->event_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); c->event_pool.push_back(e); }
+        return c->event_pool[c->event_used++];
+    }
+    StageTimer(ptb_ctx* c, int s) : ctx(c), stage(s) { if (c->timing) { a = take(c); b = take(c); cudaEventRecord(a, c->stream); } }
+    ~StageTimer() { if (ctx->timing) { cudaEventRecord(b, ctx->stream); ctx->timed.push_back({ stage, { a, b } }); } }
+};
+
+static size_t trace8_smem() { return 16 + (size_t)PTB_TLAS_STAGE_MAX_NODES * 80 + (size_t)PTB_SM_STACK * PTB_TRACE_BLOCK * sizeof(uint2); }
+
+extern "C" int ptb_render(ptb_ctx* ctx, int sample_index) {
+    if (!ctx) return PTB_E_BADARG;
+    if (!ctx->has_scene) return PTB_E_NOSCENE;
+    CK(cudaSetDevice(ctx->device));
+    const Frame& F = ctx->F;
+    cudaStream_t st = ctx->stream;
+    if (ctx->timing) { ctx->timed.clear(); ctx->event_used = 0; }
+    const int g1d = grid_for(ctx, 8);
+    const int gtrace = grid_for(ctx, PTB_TRACE_MIN_BLOCKS);
+    const bool nee = ctx->has_lights && F.config.enable_next_event_estimation;
+
+    k_begin_pass<<<1, 256, 0, st>>>(F); ctx->launches++;
+    { StageTimer t(ctx, ST_GENERATE); k_generate<<<g1d, 256, 0, st>>>(F, sample_index); ctx->launches++; }
+    for (int bounce = 0; bounce < F.config.num_bounces; bounce++) {
+        { StageTimer t(ctx, ST_TRACE);
+          if (ctx->bvh_kind == 8) k_trace8<false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce);
+          else                    k_trace2<false><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
+          ctx->launches++; }
+        { StageTimer t(ctx, ST_SORT); k_sort<<<g1d, 256, 0, st>>>(F, bounce, sample_index); ctx->launches++; }
+        { StageTimer t(ctx, ST_SHADE);
+          if (ctx->has_type[0]) { k_shade<BSDFDiffuse><<<g1d, 256, 0, st>>>(F, bounce, sample_index); ctx->launches++; }
+          if (ctx->has_type[1]) { k_shade<BSDFPlastic><<<g1d, 256, 0, st>>>(F, bounce, sample_index); ctx->launches++; }
+          if (ctx->has_type[2]) { k_shade<BSDFDielectric><<<g1d, 256, 0, st>>>(F, bounce, sample_index); ctx->launches++; }
+          if (ctx->has_type[3]) { k_shade<BSDFConductor><<<g1d, 256, 0, st>>>(F, bounce, sample_index); ctx->launches++; } }
+        if (nee) {
+            StageTimer t(ctx, ST_SHADOW);
+            if (ctx->bvh_kind == 8) k_trace8<true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce);
+            else                    k_trace2<true><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
+            ctx->launches++;
+        }
+    }
+
+    { StageTimer t(ctx, ST_POST);
+      if (F.config.enable_svgf) {
+          int e = launch_svgf(ctx->F, st, sample_index, g1d, &ctx->launches); if (e) return e;
+      } else {
+          k_accumulate<<<g1d, 256, 0, st>>>(F, float(sample_index)); ctx->launches++;
+      } }
+    k_fold_counters<<<1, PTB_MAX_BOUNCES, 0, st>>>(F); ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->last_sample_index = sample_index;
+    ctx->frames_since_reset++;
+    return 0;
+}
+
+extern "C" int ptb_sync(ptb_ctx* ctx) {
+    if (!ctx) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->timing && !ctx->timed.empty()) {
+        for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.0f;
+        for (auto& t : ctx->timed) { float ms = 0.0f; cudaEventElapsedTime(&ms, t.second.first, t.second.second); ctx->stage_ms[t.first] += ms; }
+        ctx->timed.clear();
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- readback
+extern "C" int ptb_get_aov(ptb_ctx* ctx, int aov_type, int accumulated, void** device_ptr, int* pitch) {
+    if (!ctx || aov_type < 0 || aov_type >= PTB_AOV_COUNT || !device_ptr) return PTB_E_BADARG;
+    float4* p = accumulated ? ctx->F.aov[aov_type].acc : ctx->F.aov[aov_type].fb;
+    if (!p) return PTB_E_STATE;
+    *device_ptr = p;
+    if (pitch) *pitch = ctx->F.pitch;
+    return 0;
+}
+extern "C" int ptb_get_display(ptb_ctx* ctx, void** device_ptr, int* pitch) {
+    if (!ctx || !device_ptr) return PTB_E_BADARG;
+    *device_ptr = ctx->F.display;
+    if (pitch) *pitch = ctx->F.pitch;
+    return 0;
+}
+extern "C" int ptb_download(ptb_ctx* ctx, int aov_type, int accumulated, float* host_dst) {
+    if (!ctx || !host_dst) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    void* src = nullptr;
+    if (aov_type < 0) src = ctx->F.display;
+    else { int e = ptb_get_aov(ctx, aov_type, accumulated, &src, nullptr); if (e) return e; }
+    CK(cudaMemcpyAsync(host_dst, src, (size_t)ctx->F.pitch * ctx->F.height * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int ptb_get_ray_stats(ptb_ctx* ctx, ptb_ray_stats* out, int reset) {
+    if (!ctx || !out) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    static_assert(sizeof(RayTotals) == sizeof(ptb_ray_stats), "ray stats layout");
+    CK(cudaMemcpyAsync(out, ctx->F.totals, sizeof(RayTotals), cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) CK(cudaMemsetAsync(ctx->F.totals, 0, sizeof(RayTotals), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int ptb_get_stream(ptb_ctx* ctx, void** stream) {
+    if (!ctx || !stream) return PTB_E_BADARG;
+    *stream = ctx->stream;
+    return 0;
+}
+extern "C" int ptb_export_rows(ptb_ctx* ctx, int aov_type, void* device_dst, int* owned_rows) {
+    if (!ctx || !device_dst) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    const float4* src = aov_type < 0 ? ctx->F.display : ctx->F.aov[aov_type].acc;
+    if (!src) return PTB_E_STATE;
+    k_export_rows<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->F, src, static_cast<float4*>(device_dst)); ctx->launches++;
+    if (owned_rows) *owned_rows = ctx->owned_rows;
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int ptb_assemble_rows(ptb_ctx* ctx, const void* device_src, int max_rows, void* device_dst) {
+    if (!ctx || !device_src || !device_dst) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    k_assemble_rows<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->F, static_cast<const float4*>(device_src), max_rows, static_cast<float4*>(device_dst)); ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int ptb_debug_read(ptb_ctx* ctx, int which, void* host_dst, int64_t bytes) {
+    if (!ctx || !host_dst) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    if (which == 0) {
+        size_t need = (size_t)ctx->F.pitch * ctx->F.height * sizeof(uint4);
+        if ((size_t)bytes < need) return PTB_E_BADARG;
+        CK(cudaMemsetAsync(ctx->tap_hits, 0xff, need, ctx->stream));
+        k_tap_primary_hits<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->F, ctx->tap_hits); ctx->launches++;
+        CK(cudaMemcpyAsync(host_dst, ctx->tap_hits, need, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    if (which == 1) {   // per-bounce counters of the last pass
+        if ((size_t)bytes < sizeof(Counters)) return PTB_E_BADARG;
+        CK(cudaMemcpyAsync(host_dst, ctx->F.counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    return PTB_E_BADARG;
+}
+extern "C" int64_t ptb_launch_count(ptb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int ptb_set_timing(ptb_ctx* ctx, int enabled) { if (!ctx) return PTB_E_BADARG; ctx->timing = enabled != 0; return 0; }
+extern "C" int ptb_get_stage_ms(ptb_ctx* ctx, float* ms, int n) {
+    if (!ctx || !ms) return PTB_E_BADARG;
+    for (int i = 0; i < n && i < ST_COUNT; i++) ms[i] = ctx->stage_ms[i];
+    return 0;
+}
+extern "C" const char* ptb_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : nullptr; }
+extern "C" const char* ptb_error_string(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case PTB_E_BADARG: return "bad argument";
+        case PTB_E_NOSCENE: return "no scene uploaded";
+        case PTB_E_STATE: return "invalid state or allocation failure";
+        default: return code > 0 && code < 1000 ? cudaGetErrorString((cudaError_t)code) : "CUDA driver error";
+    }
+}

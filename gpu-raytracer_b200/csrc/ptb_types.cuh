@@ -1,0 +1,144 @@
+// Device-visible structures of the B200 wavefront path tracer.
+//
+// Unlike the reference (some 60 module globals set by name, Integrator.cpp:15-30 / Pathtracer.cpp:16-38),
+// every kernel receives ONE `Frame` by value as a __grid_constant__ parameter: pointers into HBM,
+// the 44-byte GPUConfig and the 60-byte camera.  Ray streams are SoA of 16-byte vectors so every
+// queue access is a single 128-bit transaction per lane (coalesced 512 B per warp):
+//
+//   RayQueue   od0 = (origin.xyz, dir.x)  od1 = (dir.y, dir.z, cone_angle, cone_width)
+//              hit = (mesh_id, triangle_id, t bits, u16|v16<<16)      (layout of Buffers.h:28-32)
+//              path = (throughput.xyz, last_pdf)   pix = pixel_index | flags   medium = medium id
+//   ShadowQueue od0 = (origin.xyz, dir.x)  od1 = (dir.y, dir.z, max_distance, pixel_index bits)
+//              illum = (illumination.xyz, -)
+//   material queues hold 4-byte INDICES into the current RayQueue (compaction by index: the sort pass moves
+//   4 bytes per surviving ray instead of re-writing a 52-byte payload like Pathtracer.cu:426-456).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ptb.h"
+
+#define PTB_MAX_BOUNCES 128          // also a multiplier inside the RNG hash (Sampling.h:46) -- must stay 128
+#define PTB_PMJ_SEQUENCES 64
+#define PTB_PMJ_SAMPLES 4096
+#define PTB_BLUE_NOISE_TEXTURES 16
+#define PTB_BLUE_NOISE_DIM 128
+
+#define PTB_FLAG_ALLOW_NEE (1u << 31)
+#define PTB_FLAG_INSIDE_MEDIUM (1u << 30)
+#define PTB_FLAGS_ALL (PTB_FLAG_ALLOW_NEE | PTB_FLAG_INSIDE_MEDIUM)
+
+#define PTB_LUT_DIELECTRIC_DIM 16
+#define PTB_LUT_DIELECTRIC_MIN_IOR 1.0001f
+#define PTB_LUT_DIELECTRIC_MAX_IOR 2.5f
+#define PTB_LUT_CONDUCTOR_DIM 32
+
+enum { PTB_MAT_LIGHT = 0, PTB_MAT_DIFFUSE = 1, PTB_MAT_PLASTIC = 2, PTB_MAT_DIELECTRIC = 3, PTB_MAT_CONDUCTOR = 4 };
+
+struct RayQueue {
+    float4*   od0;
+    float4*   od1;
+    uint4*    hit;
+    float4*   path;
+    unsigned* pix;
+    int*      medium;
+};
+
+struct ShadowQueue {
+    float4* od0;
+    float4* od1;
+    float4* illum;
+};
+
+// per-bounce queue sizes; all bounces kept so one reset per frame suffices (same idea as Pathtracer.cu:100-116)
+struct Counters {
+    int trace[PTB_MAX_BOUNCES];
+    int mat[4][PTB_MAX_BOUNCES];     // diffuse, plastic, dielectric, conductor
+    int shadow[PTB_MAX_BOUNCES];
+    int retired[PTB_MAX_BOUNCES];
+    int retired_shadow[PTB_MAX_BOUNCES];
+};
+
+struct RayTotals {                    // 64-bit running sums for Mrays/s, folded in by k_fold_counters
+    unsigned long long trace[PTB_MAX_BOUNCES];
+    unsigned long long shadow[PTB_MAX_BOUNCES];
+    unsigned long long mat[4];
+    unsigned long long frames;
+};
+
+struct AOVBuffers {
+    float4* fb;   // written during the current pass
+    float4* acc;  // running mean over passes
+};
+
+struct TextureEntry {                 // 16 bytes, Integrator.h:129-132
+    cudaTextureObject_t tex;
+    float lod_bias;
+    float pad;
+};
+
+struct SVGFBuffers {
+    float4* gbuf_normal_depth;        // (oct normal.xy, depth, depth gradient)
+    int2*   gbuf_ids;                 // (mesh id, triangle id)
+    float2* gbuf_screen_prev;         // previous-frame screen position
+    float4* moment;                   // frame_buffer_moment
+    int*    history_length;
+    float4* history_direct;
+    float4* history_indirect;
+    float4* history_moment;
+    float4* history_normal_depth;
+    float4* taa_prev;
+    float4* taa_curr;
+    float   view_projection[16];
+    float   view_projection_prev[16];
+};
+
+struct Frame {
+    // film + tile ownership (rows are dealt to ranks in interleaved bands)
+    int width, height, pitch;
+    int rank, world, band_rows;
+    int local_pixels;                 // pixels this rank traces per pass
+    ptb_config config;
+    ptb_camera camera;
+
+    RayQueue    q[2];
+    ShadowQueue sq;
+    int*        matq[4];
+    Counters*   counters;
+    RayTotals*  totals;
+    AOVBuffers  aov[PTB_AOV_COUNT];
+    float4*     display;              // what the reference writes to its GL surface
+
+    // scene
+    const float4*        triangles;   // 6 float4 per triangle
+    const float4*        nodes8;      // 5 float4 per CWBVH node
+    const float4*        nodes2;      // 2 float4 per binary node
+    int                  tlas_nodes;  // nodes8 [0, tlas_nodes) are the TLAS
+    const int*           mesh_roots;
+    const int*           mesh_material_ids;
+    const float4*        mesh_transforms;
+    const float4*        mesh_transforms_inv;
+    const float4*        mesh_transforms_prev;
+    const signed char*   material_types;
+    const float4*        materials;   // 2 float4 per material
+    const float4*        media;       // 2 float4 per medium
+    const TextureEntry*  textures;
+    cudaTextureObject_t  sky_tex;
+    float                sky_scale;
+    const float2*        pmj;
+    const uchar2*        blue_noise;
+
+    // lights
+    float        lights_total_weight;
+    const int*   light_triangle_indices;
+    const float* light_triangle_cdf;
+    int          light_mesh_count;
+    const float* light_mesh_cdf;
+    const int2*  light_mesh_triangle_span;
+    const int*   light_mesh_transform_indices;
+
+    // Kulla-Conty LUTs
+    cudaTextureObject_t lut_dielectric_dir_enter, lut_dielectric_dir_leave, lut_dielectric_enter, lut_dielectric_leave;
+    cudaTextureObject_t lut_conductor_dir, lut_conductor;
+
+    SVGFBuffers svgf;
+};

@@ -1,0 +1,322 @@
+"""Host façade over the C ABI of include/ptb.h, shaped like the reference's Integrator / Pathtracer
+(Src/Renderer/Integrators/Integrator.h:56-296, Pathtracer.h:146-286): same entry points (`update`, `render`),
+same public state (`sample_index`, `invalidated_*`, `screen_width/height/pitch`, `get_aov`), same semantics:
+
+  * `update()` advances `sample_index` exactly like Integrator::update (Integrator.cpp:518-526): any invalidation
+    resets it to 0, otherwise it increments; `render()` then traces ONE pass with that sample index.
+  * with SVGF off the accumulator holds the running mean of passes 1..sample_index (pass 0 is overwritten, AOV.h:35-46).
+
+There is no CPU path: constructing a Pathtracer without the CUDA library or without a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+AOV_RADIANCE, AOV_RADIANCE_DIRECT, AOV_RADIANCE_INDIRECT, AOV_ALBEDO, AOV_NORMAL, AOV_POSITION = range(6)
+AOV_NAMES = ("radiance", "direct", "indirect", "albedo", "normal", "position")
+
+
+class PtbConfig(ctypes.Structure):
+    """GPUConfig, Src/CUDA/Common.h:39-67 (44 bytes)."""
+    _fields_ = [("reconstruction_filter", ctypes.c_int32), ("aov_mask", ctypes.c_uint32), ("num_bounces", ctypes.c_int32),
+                ("enable_mipmapping", ctypes.c_uint8), ("enable_next_event_estimation", ctypes.c_uint8),
+                ("enable_multiple_importance_sampling", ctypes.c_uint8), ("enable_russian_roulette", ctypes.c_uint8),
+                ("enable_svgf", ctypes.c_uint8), ("enable_spatial_variance", ctypes.c_uint8), ("enable_taa", ctypes.c_uint8), ("pad_", ctypes.c_uint8),
+                ("alpha_colour", ctypes.c_float), ("alpha_moment", ctypes.c_float), ("num_atrous_iterations", ctypes.c_int32),
+                ("sigma_z", ctypes.c_float), ("sigma_n", ctypes.c_float), ("sigma_l", ctypes.c_float)]
+
+
+class PtbCamera(ctypes.Structure):
+    _fields_ = [("position", ctypes.c_float * 3), ("bottom_left_corner", ctypes.c_float * 3), ("x_axis", ctypes.c_float * 3),
+                ("y_axis", ctypes.c_float * 3), ("pixel_spread_angle", ctypes.c_float), ("aperture_radius", ctypes.c_float),
+                ("focal_distance", ctypes.c_float)]
+
+
+class PtbTexture(ctypes.Structure):
+    _fields_ = [("format", ctypes.c_int32), ("width", ctypes.c_int32), ("height", ctypes.c_int32), ("num_levels", ctypes.c_int32),
+                ("levels", ctypes.POINTER(ctypes.c_void_p)), ("lod_bias", ctypes.c_float)]
+
+
+class PtbScene(ctypes.Structure):
+    _fields_ = [("triangles", ctypes.c_void_p), ("triangle_count", ctypes.c_int32),
+                ("bvh_nodes", ctypes.c_void_p), ("bvh_node_count", ctypes.c_int32), ("bvh_kind", ctypes.c_int32), ("tlas_node_count", ctypes.c_int32),
+                ("mesh_count", ctypes.c_int32), ("mesh_bvh_root_indices", ctypes.c_void_p), ("mesh_material_ids", ctypes.c_void_p),
+                ("mesh_transforms", ctypes.c_void_p), ("mesh_transforms_inv", ctypes.c_void_p), ("mesh_transforms_prev", ctypes.c_void_p),
+                ("material_count", ctypes.c_int32), ("material_types", ctypes.c_void_p), ("materials", ctypes.c_void_p),
+                ("medium_count", ctypes.c_int32), ("media", ctypes.c_void_p),
+                ("texture_count", ctypes.c_int32), ("textures", ctypes.POINTER(PtbTexture)),
+                ("sky", ctypes.c_void_p), ("sky_width", ctypes.c_int32), ("sky_height", ctypes.c_int32), ("sky_scale", ctypes.c_float),
+                ("pmj_samples", ctypes.c_void_p), ("blue_noise", ctypes.c_void_p),
+                ("lights_total_weight", ctypes.c_float), ("light_triangle_count", ctypes.c_int32),
+                ("light_triangle_indices", ctypes.c_void_p), ("light_triangle_cumulative_probability", ctypes.c_void_p),
+                ("light_mesh_count", ctypes.c_int32), ("light_mesh_cumulative_probability", ctypes.c_void_p),
+                ("light_mesh_triangle_span", ctypes.c_void_p), ("light_mesh_transform_indices", ctypes.c_void_p)]
+
+
+class PtbRayStats(ctypes.Structure):
+    _fields_ = [("trace", ctypes.c_uint64 * 128), ("shadow", ctypes.c_uint64 * 128), ("shaded", ctypes.c_uint64 * 4), ("frames", ctypes.c_uint64)]
+
+
+# every symbol include/ptb.h declares (tests check the built library exports exactly these)
+ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render",
+               "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_download", "ptb_get_ray_stats", "ptb_get_stream", "ptb_export_rows",
+               "ptb_assemble_rows", "ptb_debug_read", "ptb_launch_count", "ptb_set_timing", "ptb_get_stage_ms", "ptb_stage_name",
+               "ptb_error_string"]
+
+_lib = None
+
+
+def lib():
+    """Loads libptb.so (building it if stale). Raises if it cannot be built or loaded -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        path = _build.build_cuda()
+        l = ctypes.CDLL(path)
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        l.ptb_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, ci]
+        l.ptb_destroy.argtypes = [vp]; l.ptb_destroy.restype = None
+        l.ptb_upload_scene.argtypes = [vp, ctypes.POINTER(PtbScene)]
+        l.ptb_set_config.argtypes = [vp, ctypes.POINTER(PtbConfig)]
+        l.ptb_set_camera.argtypes = [vp, ctypes.POINTER(PtbCamera), vp, vp]
+        l.ptb_update_instances.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
+        l.ptb_render.argtypes = [vp, ci]
+        l.ptb_sync.argtypes = [vp]
+        l.ptb_get_aov.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(ci)]
+        l.ptb_get_display.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci)]
+        l.ptb_download.argtypes = [vp, ci, ci, vp]
+        l.ptb_get_ray_stats.argtypes = [vp, ctypes.POINTER(PtbRayStats), ci]
+        l.ptb_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
+        l.ptb_export_rows.argtypes = [vp, ci, vp, ctypes.POINTER(ci)]
+        l.ptb_assemble_rows.argtypes = [vp, vp, ci, vp]
+        l.ptb_debug_read.argtypes = [vp, ci, vp, ctypes.c_int64]
+        l.ptb_launch_count.argtypes = [vp]; l.ptb_launch_count.restype = ctypes.c_int64
+        l.ptb_set_timing.argtypes = [vp, ci]
+        l.ptb_get_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ci]
+        l.ptb_stage_name.argtypes = [ci]; l.ptb_stage_name.restype = ctypes.c_char_p
+        l.ptb_error_string.argtypes = [ci]; l.ptb_error_string.restype = ctypes.c_char_p
+        _lib = l
+    return _lib
+
+
+class PtbError(RuntimeError):
+    pass
+
+
+def _check(code, what):
+    if code != 0:
+        raise PtbError(f"{what} failed: {code} ({lib().ptb_error_string(code).decode()})")
+
+
+def default_config(**over) -> PtbConfig:
+    c = PtbConfig(2, 1, 10, 1, 1, 1, 1, 0, 1, 1, 0, 0.1, 0.1, 6, 4.0, 16.0, 10.0)
+    for k, v in over.items():
+        setattr(c, k, v)
+    return c
+
+
+def fill_scene_struct(blob, keep):
+    """Builds a PtbScene pointing into the blob's numpy arrays (`keep` must outlive the call that consumes it)."""
+    def arr(key, dtype=None):
+        a = np.ascontiguousarray(blob[key] if dtype is None else np.asarray(blob[key]).astype(dtype, copy=False))
+        keep.append(a)
+        return a.ctypes.data
+    s = PtbScene()
+    node_bytes = 80 if int(blob["bvh_kind"]) == 8 else 32
+    s.triangles = arr("triangles"); s.triangle_count = int(blob["triangles"].shape[0])
+    s.bvh_nodes = arr("bvh_nodes"); s.bvh_node_count = int(blob["bvh_nodes"].size // node_bytes)
+    s.bvh_kind = int(blob["bvh_kind"]); s.tlas_node_count = int(blob["tlas_node_count"])
+    s.mesh_count = int(blob["mesh_bvh_root_indices"].size)
+    s.mesh_bvh_root_indices = arr("mesh_bvh_root_indices"); s.mesh_material_ids = arr("mesh_material_ids")
+    s.mesh_transforms = arr("mesh_transforms"); s.mesh_transforms_inv = arr("mesh_transforms_inv"); s.mesh_transforms_prev = arr("mesh_transforms_prev")
+    s.material_count = int(blob["material_types"].size); s.material_types = arr("material_types"); s.materials = arr("materials")
+    s.medium_count = int(blob["media"].shape[0]); s.media = arr("media")
+    texs = blob["textures"]
+    s.texture_count = len(texs)
+    if texs:
+        tarr = (PtbTexture * len(texs))()
+        for i, t in enumerate(texs):
+            levels = [np.ascontiguousarray(l, dtype=np.uint8) for l in t["levels"]]
+            keep.extend(levels)
+            ptrs = (ctypes.c_void_p * len(levels))(*[l.ctypes.data for l in levels])
+            keep.append(ptrs)
+            tarr[i].format = 1 if t["format"] == "bc1" else 0
+            tarr[i].width, tarr[i].height, tarr[i].num_levels = int(t["width"]), int(t["height"]), len(levels)
+            tarr[i].levels = ctypes.cast(ptrs, ctypes.POINTER(ctypes.c_void_p)); tarr[i].lod_bias = float(t["lod_bias"])
+        keep.append(tarr)
+        s.textures = ctypes.cast(tarr, ctypes.POINTER(PtbTexture))
+    sky = np.ascontiguousarray(blob["sky"], dtype=np.float32); keep.append(sky)
+    s.sky = sky.ctypes.data; s.sky_height, s.sky_width = sky.shape[:2]; s.sky_scale = float(blob["sky_scale"])
+    s.pmj_samples = arr("pmj"); s.blue_noise = arr("blue_noise")
+    s.lights_total_weight = float(blob["lights_total_weight"])
+    s.light_triangle_count = int(blob["light_triangle_indices"].size)
+    s.light_triangle_indices = arr("light_triangle_indices"); s.light_triangle_cumulative_probability = arr("light_triangle_cdf")
+    s.light_mesh_count = int(blob["light_mesh_cdf"].size); s.light_mesh_cumulative_probability = arr("light_mesh_cdf")
+    s.light_mesh_triangle_span = arr("light_mesh_triangle_span"); s.light_mesh_transform_indices = arr("light_mesh_transform_indices")
+    return s
+
+
+def camera_struct(cam15) -> PtbCamera:
+    c = PtbCamera()
+    v = [float(x) for x in cam15]
+    for i in range(3):
+        c.position[i] = v[i]; c.bottom_left_corner[i] = v[3 + i]; c.x_axis[i] = v[6 + i]; c.y_axis[i] = v[9 + i]
+    c.pixel_spread_angle, c.aperture_radius, c.focal_distance = v[12], v[13], v[14]
+    return c
+
+
+class Pathtracer:
+    """Integrator-shaped handle: `update()` then `render()` once per frame, like Src/Main.cpp:137-138."""
+
+    def __init__(self, blob, width=None, height=None, device=0, rank=0, world=1, band_rows=8, config: PtbConfig | None = None):
+        l = lib()
+        self.screen_width = int(width or blob["width"]); self.screen_height = int(height or blob["height"])
+        self.screen_pitch = (self.screen_width + 31) // 32 * 32
+        if (self.screen_width, self.screen_height) != (int(blob["width"]), int(blob["height"])):
+            raise ValueError("the blob's camera block was built for a different film size; rebuild it with build_blob(width=, height=)")
+        self._ctx = ctypes.c_void_p()
+        _check(l.ptb_create(ctypes.byref(self._ctx), device, self.screen_width, self.screen_height, rank, world, band_rows), "ptb_create")
+        self.rank, self.world, self.band_rows = rank, world, band_rows
+        keep = []
+        scene = fill_scene_struct(blob, keep)
+        _check(l.ptb_upload_scene(self._ctx, ctypes.byref(scene)), "ptb_upload_scene")
+        self.gpu_config = config or default_config(num_bounces=int(blob["num_bounces"]))
+        self._camera = camera_struct(blob["camera"])
+        self._view_projection = np.ascontiguousarray(blob["view_projection"], dtype=np.float32)
+        self._view_projection_prev = self._view_projection.copy()
+        self.sample_index = 0
+        self.invalidated_scene = False      # TLAS is uploaded with the scene; set + call update_instances() to change it
+        self.invalidated_camera = True
+        self.invalidated_gpu_config = True
+        self._first = True
+
+    # ---- Integrator::update (Integrator.cpp:432-528)
+    def update(self, delta=0.0):
+        l = lib()
+        if self.invalidated_gpu_config and self.gpu_config.enable_svgf and self._camera.aperture_radius > 0.0:
+            self._camera.aperture_radius = 0.0      # "SVGF and DoF cannot simultaneously be enabled" (Integrator.cpp:433-437)
+            self.invalidated_camera = True
+        camera_moved = self.invalidated_camera
+        if self.invalidated_camera:
+            _check(l.ptb_set_camera(self._ctx, ctypes.byref(self._camera), self._view_projection.ctypes.data, self._view_projection_prev.ctypes.data), "ptb_set_camera")
+            if not self.gpu_config.enable_svgf:
+                self.sample_index = 0
+            self.invalidated_camera = False
+        elif self.gpu_config.enable_svgf:
+            # static camera: view_projection_prev catches up with view_projection (Camera.cpp:90)
+            _check(l.ptb_set_camera(self._ctx, ctypes.byref(self._camera), self._view_projection.ctypes.data, self._view_projection.ctypes.data), "ptb_set_camera")
+        if self.invalidated_gpu_config:
+            self.invalidated_gpu_config = False
+            self.sample_index = 0
+            _check(l.ptb_set_config(self._ctx, ctypes.byref(self.gpu_config)), "ptb_set_config")
+        elif camera_moved and not self.gpu_config.enable_svgf:
+            self.sample_index = 0
+        else:
+            self.sample_index += 1
+
+    def set_camera(self, cam15, view_projection=None):
+        self._view_projection_prev = self._view_projection.copy()
+        self._camera = camera_struct(cam15)
+        if view_projection is not None:
+            self._view_projection = np.ascontiguousarray(view_projection, dtype=np.float32)
+        self.invalidated_camera = True
+
+    # ---- Pathtracer::render (Pathtracer.cpp:738-855)
+    def render(self):
+        _check(lib().ptb_render(self._ctx, int(self.sample_index)), "ptb_render")
+
+    def render_pass(self, sample_index):
+        """Direct control for tests: one pass with an explicit sample index (no Integrator bookkeeping)."""
+        if self.invalidated_camera or self.invalidated_gpu_config:
+            keep = self.sample_index
+            self.update(); self.sample_index = keep
+        _check(lib().ptb_render(self._ctx, int(sample_index)), "ptb_render")
+
+    def sync(self):
+        _check(lib().ptb_sync(self._ctx), "ptb_sync")
+
+    def render_frames(self, passes):
+        """sample_index 0..passes -> accumulator = mean of passes 1..passes (the reference's `-N passes` capture)."""
+        for _ in range(passes + 1):
+            self.update(); self.render()
+        self.sync()
+
+    # ---- readback
+    def get_aov(self, aov_type, accumulated=True):
+        out = np.empty((self.screen_height, self.screen_pitch, 4), dtype=np.float32)
+        _check(lib().ptb_download(self._ctx, int(aov_type), int(accumulated), out.ctypes.data), "ptb_download")
+        return out
+
+    def get_display(self):
+        out = np.empty((self.screen_height, self.screen_pitch, 4), dtype=np.float32)
+        _check(lib().ptb_download(self._ctx, -1, 1, out.ctypes.data), "ptb_download")
+        return out
+
+    def aov_device_ptr(self, aov_type, accumulated=True):
+        p, pitch = ctypes.c_void_p(), ctypes.c_int()
+        _check(lib().ptb_get_aov(self._ctx, aov_type, int(accumulated), ctypes.byref(p), ctypes.byref(pitch)), "ptb_get_aov")
+        return p.value, pitch.value
+
+    def display_device_ptr(self):
+        p, pitch = ctypes.c_void_p(), ctypes.c_int()
+        _check(lib().ptb_get_display(self._ctx, ctypes.byref(p), ctypes.byref(pitch)), "ptb_get_display")
+        return p.value, pitch.value
+
+    def stream(self):
+        p = ctypes.c_void_p()
+        _check(lib().ptb_get_stream(self._ctx, ctypes.byref(p)), "ptb_get_stream")
+        return p.value or 0
+
+    def export_rows(self, device_dst, aov_type=AOV_RADIANCE):
+        rows = ctypes.c_int()
+        _check(lib().ptb_export_rows(self._ctx, aov_type, ctypes.c_void_p(device_dst), ctypes.byref(rows)), "ptb_export_rows")
+        return rows.value
+
+    def assemble_rows(self, device_src, max_rows, device_dst):
+        _check(lib().ptb_assemble_rows(self._ctx, ctypes.c_void_p(device_src), int(max_rows), ctypes.c_void_p(device_dst)), "ptb_assemble_rows")
+
+    def owned_rows(self):
+        return sum(1 for y in range(self.screen_height) if (y // self.band_rows) % self.world == self.rank)
+
+    def ray_stats(self, reset=False):
+        st = PtbRayStats()
+        _check(lib().ptb_get_ray_stats(self._ctx, ctypes.byref(st), int(reset)), "ptb_get_ray_stats")
+        return dict(trace=np.array(st.trace[:], dtype=np.uint64), shadow=np.array(st.shadow[:], dtype=np.uint64),
+                    shaded=np.array(st.shaded[:], dtype=np.uint64), frames=int(st.frames))
+
+    def primary_hits(self):
+        out = np.empty((self.screen_height, self.screen_pitch, 4), dtype=np.uint32)
+        _check(lib().ptb_debug_read(self._ctx, 0, out.ctypes.data, out.nbytes), "ptb_debug_read")
+        return out
+
+    def last_pass_counters(self):
+        out = np.empty(8 * 128, dtype=np.int32)
+        _check(lib().ptb_debug_read(self._ctx, 1, out.ctypes.data, out.nbytes), "ptb_debug_read")
+        o = out.reshape(8, 128)
+        return dict(trace=o[0], diffuse=o[1], plastic=o[2], dielectric=o[3], conductor=o[4], shadow=o[5])
+
+    def launch_count(self):
+        return int(lib().ptb_launch_count(self._ctx))
+
+    def set_timing(self, on=True):
+        _check(lib().ptb_set_timing(self._ctx, int(on)), "ptb_set_timing")
+
+    def stage_ms(self):
+        ms = (ctypes.c_float * 6)()
+        _check(lib().ptb_get_stage_ms(self._ctx, ms, 6), "ptb_get_stage_ms")
+        return {lib().ptb_stage_name(i).decode(): float(ms[i]) for i in range(6)}
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            lib().ptb_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,576 @@
+// ref_harness.cpp -- headless driver for the REFERENCE's own kernels.  TEST / BASELINE INFRASTRUCTURE ONLY.
+//
+// The reference (jan-van-bergen/GPU-Raytracer) is a Windows + OpenGL desktop program whose host code does not build
+// with g++.  Its device code does: oracle/Makefile compiles Src/CUDA/Pathtracer.cu UNMODIFIED,
+// from where it lies under /root/reference, into oracle/_ref/pathtracer_ref.cubin with the reference's own NVRTC
+// flag set (Src/Device/CUDAModule.cpp:151-160).  This file is OUR host code that loads that cubin with the CUDA
+// driver API, sets the module globals the reference's host sets by name (face 2) and replays
+// the launch sequence of Pathtracer::render() (Src/Renderer/Integrators/Pathtracer.cpp:738-855) with the reference's
+// launch recipe: 256-thread 1-D kernels at full BATCH_SIZE width (Pathtracer.cpp:116-121,284-289), persistent trace
+// kernels sized by cuOccupancyMaxPotentialBlockSize with an 8-entry shared stack (Integrator.h:280-295), PREFER_L1
+// (CUDAKernel.h:30-31), pixel batches of BATCH_SIZE with a blocking buffer_sizes reset between them.
+//
+// It is the parity checker for the product kernels ("the reference itself, run here") and the `--impl reference`
+// arm of bench.py.  Nothing under gpu-raytracer_b200/ depends on it.
+#include <cuda.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../include/ptb.h"   // only for the plain-C scene/config/camera structs
+
+#define RCK(expr) do { CUresult r__ = (expr); if (r__ != CUDA_SUCCESS) { const char* s__ = nullptr; cuGetErrorString(r__, &s__); \
+    fprintf(stderr, "[ref] %s failed: %d (%s)\n", #expr, (int)r__, s__ ? s__ : "?"); return 1000 + (int)r__; } } while (0)
+
+static const int BATCH_SIZE = 1080 * 720;   // Common.h:69-71
+static const int MAX_BOUNCES = 128;
+static const int SHARED_STACK_SIZE = 8;
+
+struct BufferSizes {   // Pathtracer.h:121-144
+    int trace[MAX_BOUNCES], diffuse[MAX_BOUNCES], plastic[MAX_BOUNCES], dielectric[MAX_BOUNCES], conductor[MAX_BOUNCES], shadow[MAX_BOUNCES];
+    int rays_retired[MAX_BOUNCES], rays_retired_shadow[MAX_BOUNCES];
+    void reset(int batch) { memset(this, 0, sizeof(*this)); trace[0] = batch; }
+};
+
+struct Kernel {
+    CUfunction fn = nullptr;
+    unsigned gx = 1, gy = 1, bx = 1, by = 1, smem = 0;
+};
+
+struct ref_ctx {
+    CUcontext cu = nullptr;
+    CUmodule mod = nullptr;
+    int width = 0, height = 0, pitch = 0, pixel_count = 0;
+    ptb_config config;
+    int bvh_kind = 8;
+    bool has_type[4] = { false, false, false, false };
+    bool has_lights = false;
+    Kernel generate, trace, trace_shadow, sort, material[4], accumulate;
+    Kernel svgf_reproject, svgf_variance, svgf_atrous, svgf_finalize, taa, taa_finalize;
+    Kernel integrate_dielectric, average_dielectric, integrate_conductor, average_conductor;
+    CUdeviceptr aov_fb[6] = {}, aov_acc[6] = {};
+    CUarray surf_array = nullptr; CUsurfObject surf = 0;
+    std::vector<CUdeviceptr> allocs;
+    CUdeviceptr trace_hits[2] = {}, trace_pix[2] = {};
+    BufferSizes sizes;
+    uint64_t total_trace[MAX_BOUNCES] = {}, total_shadow[MAX_BOUNCES] = {}, total_shaded[4] = {}, frames = 0;
+    bool svgf_ready = false;
+    CUdeviceptr history_ptrs[5] = {};
+    bool timing = false;
+    std::vector<CUevent> events; size_t ev_used = 0;
+    std::vector<std::pair<int, std::pair<CUevent, CUevent>>> timed;
+    float stage_ms[6] = {};
+};
+
+static int get_global(ref_ctx* c, const char* name, CUdeviceptr* p, size_t* sz) {
+    RCK(cuModuleGetGlobal(p, sz, c->mod, name));
+    return 0;
+}
+template <typename T>
+static int set_global(ref_ctx* c, const char* name, const T& v) {
+    CUdeviceptr p; size_t sz;
+    int e = get_global(c, name, &p, &sz); if (e) return e;
+    if (sz < sizeof(T)) { fprintf(stderr, "[ref] global %s is %zu bytes, need %zu\n", name, sz, sizeof(T)); return 1; }
+    RCK(cuMemcpyHtoD(p, &v, sizeof(T)));
+    return 0;
+}
+static int dalloc(ref_ctx* c, CUdeviceptr* p, size_t bytes) {
+    RCK(cuMemAlloc(p, bytes ? bytes : 16));
+    RCK(cuMemsetD8(*p, 0, bytes ? bytes : 16));
+    c->allocs.push_back(*p);
+    return 0;
+}
+static int dupload(ref_ctx* c, CUdeviceptr* p, const void* src, size_t bytes) {
+    int e = dalloc(c, p, bytes); if (e) return e;
+    if (bytes) RCK(cuMemcpyHtoD(*p, src, bytes));
+    return 0;
+}
+static int get_kernel(ref_ctx* c, Kernel& k, const char* name) {
+    RCK(cuModuleGetFunction(&k.fn, c->mod, name));
+    cuFuncSetCacheConfig(k.fn, CU_FUNC_CACHE_PREFER_L1);
+    cuFuncSetSharedMemConfig(k.fn, CU_SHARED_MEM_CONFIG_EIGHT_BYTE_BANK_SIZE);
+    return 0;
+}
+static size_t smem_for_block_8(int block) { return (size_t)block * SHARED_STACK_SIZE * 8; }
+static size_t smem_for_block_4(int block) { return (size_t)block * SHARED_STACK_SIZE * 4; }
+
+static int size_trace_kernel(Kernel& k, int elem) {   // Integrator.h:280-295
+    int grid = 0, block = 0;
+    RCK(cuOccupancyMaxPotentialBlockSize(&grid, &block, k.fn, elem == 8 ? smem_for_block_8 : smem_for_block_4, 0, 0));
+    k.bx = 32; k.by = block / 32; k.gx = 1; k.gy = grid;
+    k.smem = (unsigned)(elem == 8 ? smem_for_block_8(block) : smem_for_block_4(block));
+    return 0;
+}
+static int size_2d_kernel(ref_ctx* c, Kernel& k) {    // CUDAKernel.h:67-81, Pathtracer.cpp:276-282
+    int grid = 0, block = 0;
+    RCK(cuOccupancyMaxPotentialBlockSize(&grid, &block, k.fn, nullptr, 0, 0));
+    int bx = (int)sqrt((double)block);
+    bx += (32 - bx) & 31;
+    if (bx == 0) bx = 32;
+    int by = block / bx;
+    k.bx = bx; k.by = by;
+    k.gx = c->pitch / bx; k.gy = (c->height + by - 1) / by;
+    return 0;
+}
+static void size_1d_kernel(Kernel& k) { k.bx = 256; k.by = 1; k.gx = (BATCH_SIZE + 255) / 256; k.gy = 1; }
+
+static int launch(ref_ctx* c, const Kernel& k, void** args) {
+    RCK(cuLaunchKernel(k.fn, k.gx, k.gy, 1, k.bx, k.by, 1, k.smem, nullptr, args, nullptr));
+    return 0;
+}
+
+struct DevSoA3 { CUdeviceptr x, y, z; };
+struct DevTraceBuffer { DevSoA3 origin, direction; CUdeviceptr hits, cone_angle, cone_width, medium, pixel_index_and_flags; DevSoA3 throughput; CUdeviceptr last_pdf; };
+struct DevMaterialBuffer { DevSoA3 direction; CUdeviceptr hits, cone_angle, cone_width, medium, pixel_index; DevSoA3 throughput; };
+struct DevShadowBuffer { DevSoA3 origin, direction; CUdeviceptr max_distance, illumination_and_pixel_index; };
+struct DevAOV { CUdeviceptr framebuffer, accumulator; };
+struct DevTexture { CUtexObject tex; float lod_bias; float pad; };
+
+static int alloc_soa(ref_ctx* c, DevSoA3& s, size_t n) { return dalloc(c, &s.x, n * 4) || dalloc(c, &s.y, n * 4) || dalloc(c, &s.z, n * 4); }
+
+extern "C" {
+
+int ref_create(ref_ctx** out, const char* cubin_path, int device, int width, int height) {
+    ref_ctx* c = new ref_ctx();
+    RCK(cuInit(0));
+    CUdevice dev;
+    RCK(cuDeviceGet(&dev, device));
+    RCK(cuDevicePrimaryCtxRetain(&c->cu, dev));
+    RCK(cuCtxSetCurrent(c->cu));
+    RCK(cuModuleLoad(&c->mod, cubin_path));
+    c->width = width; c->height = height; c->pitch = (width + 31) / 32 * 32; c->pixel_count = width * height;
+    memset(&c->config, 0, sizeof(c->config));
+    *out = c;
+    return 0;
+}
+
+void ref_destroy(ref_ctx* c) {
+    if (!c) return;
+    cuCtxSetCurrent(c->cu);
+    cuCtxSynchronize();
+    for (CUdeviceptr p : c->allocs) cuMemFree(p);
+    if (c->surf) cuSurfObjectDestroy(c->surf);
+    if (c->surf_array) cuArrayDestroy(c->surf_array);
+    for (CUevent e : c->events) cuEventDestroy(e);
+    if (c->mod) cuModuleUnload(c->mod);
+    delete c;
+}
+
+static int make_texture(const ptb_texture& t, CUtexObject* tex) {   // Integrator.cpp:42-94
+    const bool bc1 = t.format == 1;
+    const int aw = bc1 ? (t.width + 3) / 4 : t.width, ah = bc1 ? (t.height + 3) / 4 : t.height;
+    CUDA_ARRAY3D_DESCRIPTOR ad; memset(&ad, 0, sizeof(ad));
+    ad.Width = aw; ad.Height = ah; ad.NumChannels = bc1 ? 2 : 4;
+    ad.Format = bc1 ? CU_AD_FORMAT_UNSIGNED_INT32 : CU_AD_FORMAT_UNSIGNED_INT8;
+    CUmipmappedArray arr;
+    RCK(cuMipmappedArrayCreate(&arr, &ad, t.num_levels));
+    for (int l = 0; l < t.num_levels; l++) {
+        CUarray level; RCK(cuMipmappedArrayGetLevel(&level, arr, l));
+        int lw = aw >> l; if (lw < 1) lw = 1;
+        int lh = ah >> l; if (lh < 1) lh = 1;
+        CUDA_MEMCPY2D cp; memset(&cp, 0, sizeof(cp));
+        cp.srcMemoryType = CU_MEMORYTYPE_HOST; cp.srcHost = t.levels[l]; cp.srcPitch = (size_t)lw * (bc1 ? 8 : 4);
+        cp.dstMemoryType = CU_MEMORYTYPE_ARRAY; cp.dstArray = level; cp.WidthInBytes = cp.srcPitch; cp.Height = lh;
+        RCK(cuMemcpy2D(&cp));
+    }
+    CUDA_RESOURCE_DESC rd; memset(&rd, 0, sizeof(rd));
+    rd.resType = CU_RESOURCE_TYPE_MIPMAPPED_ARRAY; rd.res.mipmap.hMipmappedArray = arr;
+    CUDA_TEXTURE_DESC td; memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = CU_TR_ADDRESS_MODE_WRAP; td.addressMode[2] = CU_TR_ADDRESS_MODE_CLAMP;
+    td.filterMode = CU_TR_FILTER_MODE_LINEAR; td.mipmapFilterMode = CU_TR_FILTER_MODE_LINEAR;
+    td.maxAnisotropy = 16; td.maxMipmapLevelClamp = float(t.num_levels - 1); td.flags = CU_TRSF_NORMALIZED_COORDINATES;
+    CUDA_RESOURCE_VIEW_DESC vd; memset(&vd, 0, sizeof(vd));
+    vd.format = bc1 ? CU_RES_VIEW_FORMAT_UNSIGNED_BC1 : CU_RES_VIEW_FORMAT_UINT_4X8;
+    vd.width = bc1 ? (size_t)aw * 4 : aw; vd.height = bc1 ? (size_t)ah * 4 : ah; vd.lastMipmapLevel = t.num_levels - 1;
+    RCK(cuTexObjectCreate(tex, &rd, &td, &vd));
+    return 0;
+}
+
+static int make_array_texture(CUarray arr, CUtexObject* tex) {   // CUDAMemory::create_texture, linear + clamp
+    CUDA_RESOURCE_DESC rd; memset(&rd, 0, sizeof(rd));
+    rd.resType = CU_RESOURCE_TYPE_ARRAY; rd.res.array.hArray = arr;
+    CUDA_TEXTURE_DESC td; memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = CU_TR_ADDRESS_MODE_CLAMP;
+    td.filterMode = CU_TR_FILTER_MODE_LINEAR; td.flags = CU_TRSF_NORMALIZED_COORDINATES;
+    RCK(cuTexObjectCreate(tex, &rd, &td, nullptr));
+    return 0;
+}
+static int make_surface(CUarray arr, CUsurfObject* s) {
+    CUDA_RESOURCE_DESC rd; memset(&rd, 0, sizeof(rd));
+    rd.resType = CU_RESOURCE_TYPE_ARRAY; rd.res.array.hArray = arr;
+    RCK(cuSurfObjectCreate(s, &rd));
+    return 0;
+}
+static int make_array(CUarray* arr, int w, int h, int d, int channels, CUarray_format fmt, bool surface) {
+    CUDA_ARRAY3D_DESCRIPTOR ad; memset(&ad, 0, sizeof(ad));
+    ad.Width = w; ad.Height = h; ad.Depth = d; ad.NumChannels = channels; ad.Format = fmt; ad.Flags = surface ? CUDA_ARRAY3D_SURFACE_LDST : 0;
+    RCK(cuArray3DCreate(arr, &ad));
+    return 0;
+}
+
+static int bake_luts(ref_ctx* c) {   // Pathtracer.cpp:182-245
+    int e = 0;
+    e |= get_kernel(c, c->integrate_dielectric, "kernel_integrate_dielectric"); e |= get_kernel(c, c->average_dielectric, "kernel_average_dielectric");
+    e |= get_kernel(c, c->integrate_conductor, "kernel_integrate_conductor");   e |= get_kernel(c, c->average_conductor, "kernel_average_conductor");
+    if (e) return e;
+    const char* dir_names[2] = { "lut_dielectric_directional_albedo_enter", "lut_dielectric_directional_albedo_leave" };
+    const char* avg_names[2] = { "lut_dielectric_albedo_enter", "lut_dielectric_albedo_leave" };
+    for (int pass = 0; pass < 2; pass++) {
+        CUarray a_dir, a_avg;
+        e = make_array(&a_dir, 16, 16, 16, 1, CU_AD_FORMAT_FLOAT, true); if (e) return e;
+        e = make_array(&a_avg, 16, 16, 0, 1, CU_AD_FORMAT_FLOAT, true); if (e) return e;
+        CUsurfObject s_dir, s_avg;
+        e = make_surface(a_dir, &s_dir); if (e) return e;
+        e = make_surface(a_avg, &s_avg); if (e) return e;
+        bool entering = pass == 0;
+        Kernel k = c->integrate_dielectric; k.bx = 256; k.by = 1; k.gx = (16 * 16 * 16 + 255) / 256; k.gy = 1;
+        void* a1[] = { &entering, &s_dir };
+        e = launch(c, k, a1); if (e) return e;
+        k = c->average_dielectric; k.bx = 256; k.by = 1; k.gx = 1; k.gy = 1;
+        void* a2[] = { &s_dir, &s_avg };
+        e = launch(c, k, a2); if (e) return e;
+        RCK(cuCtxSynchronize());
+        CUtexObject t_dir, t_avg;
+        e = make_array_texture(a_dir, &t_dir); if (e) return e;
+        e = make_array_texture(a_avg, &t_avg); if (e) return e;
+        e = set_global(c, dir_names[pass], t_dir); if (e) return e;
+        e = set_global(c, avg_names[pass], t_avg); if (e) return e;
+    }
+    CUdeviceptr d_dir, d_avg;
+    e = dalloc(c, &d_dir, 32 * 32 * 4); if (e) return e;
+    e = dalloc(c, &d_avg, 32 * 4); if (e) return e;
+    Kernel k = c->integrate_conductor; k.bx = 256; k.by = 1; k.gx = 4; k.gy = 1;
+    void* a1[] = { &d_dir };
+    e = launch(c, k, a1); if (e) return e;
+    RCK(cuCtxSynchronize());
+    k = c->average_conductor; k.bx = 256; k.by = 1; k.gx = 1; k.gy = 1;
+    void* a2[] = { &d_dir, &d_avg };
+    e = launch(c, k, a2); if (e) return e;
+    RCK(cuCtxSynchronize());
+    CUarray a_dir, a_avg;
+    e = make_array(&a_dir, 32, 32, 0, 1, CU_AD_FORMAT_FLOAT, false); if (e) return e;
+    e = make_array(&a_avg, 32, 0, 0, 1, CU_AD_FORMAT_FLOAT, false); if (e) return e;
+    CUDA_MEMCPY2D cp; memset(&cp, 0, sizeof(cp));
+    cp.srcMemoryType = CU_MEMORYTYPE_DEVICE; cp.srcDevice = d_dir; cp.srcPitch = 32 * 4; cp.dstMemoryType = CU_MEMORYTYPE_ARRAY; cp.dstArray = a_dir;
+    cp.WidthInBytes = 32 * 4; cp.Height = 32;
+    RCK(cuMemcpy2D(&cp));
+    cp.srcDevice = d_avg; cp.dstArray = a_avg; cp.Height = 1;
+    RCK(cuMemcpy2D(&cp));
+    CUtexObject t_dir, t_avg;
+    e = make_array_texture(a_dir, &t_dir); if (e) return e;
+    e = make_array_texture(a_avg, &t_avg); if (e) return e;
+    e = set_global(c, "lut_conductor_directional_albedo", t_dir); if (e) return e;
+    e = set_global(c, "lut_conductor_albedo", t_avg); if (e) return e;
+    return 0;
+}
+
+static int enable_aov(ref_ctx* c, int k) {
+    if (c->aov_fb[k]) return 0;
+    size_t bytes = (size_t)c->pitch * c->height * 16;
+    return dalloc(c, &c->aov_fb[k], bytes) || dalloc(c, &c->aov_acc[k], bytes);
+}
+static int push_aovs(ref_ctx* c) {
+    DevAOV aovs[6];
+    for (int i = 0; i < 6; i++) { aovs[i].framebuffer = c->aov_fb[i]; aovs[i].accumulator = c->aov_acc[i]; }
+    return set_global(c, "aovs", aovs);
+}
+
+int ref_upload_scene(ref_ctx* c, const ptb_scene* s) {
+    RCK(cuCtxSetCurrent(c->cu));
+    int e = 0;
+    c->bvh_kind = s->bvh_kind;
+    e |= set_global(c, "screen_width", c->width); e |= set_global(c, "screen_pitch", c->pitch); e |= set_global(c, "screen_height", c->height);
+    if (e) return e;
+    // kernels + launch dims (Pathtracer.cpp:76-145)
+    const char* tname = s->bvh_kind == 8 ? "kernel_trace_bvh8" : "kernel_trace_bvh2";
+    const char* sname = s->bvh_kind == 8 ? "kernel_trace_shadow_bvh8" : "kernel_trace_shadow_bvh2";
+    e |= get_kernel(c, c->generate, "kernel_generate"); e |= get_kernel(c, c->trace, tname); e |= get_kernel(c, c->trace_shadow, sname);
+    e |= get_kernel(c, c->sort, "kernel_sort"); e |= get_kernel(c, c->accumulate, "kernel_accumulate");
+    e |= get_kernel(c, c->material[0], "kernel_material_diffuse"); e |= get_kernel(c, c->material[1], "kernel_material_plastic");
+    e |= get_kernel(c, c->material[2], "kernel_material_dielectric"); e |= get_kernel(c, c->material[3], "kernel_material_conductor");
+    e |= get_kernel(c, c->svgf_reproject, "kernel_svgf_reproject"); e |= get_kernel(c, c->svgf_variance, "kernel_svgf_variance");
+    e |= get_kernel(c, c->svgf_atrous, "kernel_svgf_atrous"); e |= get_kernel(c, c->svgf_finalize, "kernel_svgf_finalize");
+    e |= get_kernel(c, c->taa, "kernel_taa"); e |= get_kernel(c, c->taa_finalize, "kernel_taa_finalize");
+    if (e) return e;
+    size_1d_kernel(c->generate); size_1d_kernel(c->sort);
+    for (int m = 0; m < 4; m++) size_1d_kernel(c->material[m]);
+    e |= size_trace_kernel(c->trace, s->bvh_kind == 8 ? 8 : 4); e |= size_trace_kernel(c->trace_shadow, s->bvh_kind == 8 ? 8 : 4);
+    e |= size_2d_kernel(c, c->accumulate); e |= size_2d_kernel(c, c->svgf_reproject); e |= size_2d_kernel(c, c->svgf_variance);
+    e |= size_2d_kernel(c, c->svgf_atrous); e |= size_2d_kernel(c, c->svgf_finalize); e |= size_2d_kernel(c, c->taa); e |= size_2d_kernel(c, c->taa_finalize);
+    if (e) return e;
+
+    // geometry
+    CUdeviceptr p;
+    e = dupload(c, &p, s->triangles, (size_t)s->triangle_count * 96); if (e) return e; e = set_global(c, "triangles", p); if (e) return e;
+    e = dupload(c, &p, s->bvh_nodes, (size_t)s->bvh_node_count * (s->bvh_kind == 8 ? 80 : 32)); if (e) return e;
+    e = set_global(c, s->bvh_kind == 8 ? "bvh8_nodes" : "bvh2_nodes", p); if (e) return e;
+    e = dupload(c, &p, s->mesh_bvh_root_indices, (size_t)s->mesh_count * 4); if (e) return e; e = set_global(c, "mesh_bvh_root_indices", p); if (e) return e;
+    e = dupload(c, &p, s->mesh_material_ids, (size_t)s->mesh_count * 4); if (e) return e; e = set_global(c, "mesh_material_ids", p); if (e) return e;
+    e = dupload(c, &p, s->mesh_transforms, (size_t)s->mesh_count * 48); if (e) return e; e = set_global(c, "mesh_transforms", p); if (e) return e;
+    e = dupload(c, &p, s->mesh_transforms_inv, (size_t)s->mesh_count * 48); if (e) return e; e = set_global(c, "mesh_transforms_inv", p); if (e) return e;
+    e = dupload(c, &p, s->mesh_transforms_prev ? s->mesh_transforms_prev : s->mesh_transforms, (size_t)s->mesh_count * 48); if (e) return e;
+    e = set_global(c, "mesh_transforms_prev", p); if (e) return e;
+    // materials, media
+    e = dupload(c, &p, s->material_types, (size_t)s->material_count); if (e) return e; e = set_global(c, "material_types", p); if (e) return e;
+    e = dupload(c, &p, s->materials, (size_t)s->material_count * 32); if (e) return e; e = set_global(c, "materials", p); if (e) return e;
+    e = dupload(c, &p, s->media, (size_t)(s->medium_count > 0 ? s->medium_count : 0) * 32); if (e) return e; e = set_global(c, "media", p); if (e) return e;
+    for (int i = 0; i < s->material_count; i++) { int t = s->material_types[i]; if (t >= 1 && t <= 4) c->has_type[t - 1] = true; }
+    // textures
+    std::vector<DevTexture> table((size_t)(s->texture_count > 0 ? s->texture_count : 0));
+    for (size_t i = 0; i < table.size(); i++) { e = make_texture(s->textures[i], &table[i].tex); if (e) return e; table[i].lod_bias = s->textures[i].lod_bias; table[i].pad = 0; }
+    e = dupload(c, &p, table.data(), table.size() * sizeof(DevTexture)); if (e) return e; e = set_global(c, "textures", p); if (e) return e;
+    // sky (Integrator.cpp:285-296)
+    {
+        CUarray arr; e = make_array(&arr, s->sky_width, s->sky_height, 0, 4, CU_AD_FORMAT_FLOAT, false); if (e) return e;
+        CUDA_MEMCPY2D cp; memset(&cp, 0, sizeof(cp));
+        cp.srcMemoryType = CU_MEMORYTYPE_HOST; cp.srcHost = s->sky; cp.srcPitch = (size_t)s->sky_width * 16;
+        cp.dstMemoryType = CU_MEMORYTYPE_ARRAY; cp.dstArray = arr; cp.WidthInBytes = cp.srcPitch; cp.Height = s->sky_height;
+        RCK(cuMemcpy2D(&cp));
+        CUtexObject tex; e = make_array_texture(arr, &tex); if (e) return e;
+        e = set_global(c, "sky_texture", tex); if (e) return e;
+        e = set_global(c, "sky_scale", s->sky_scale); if (e) return e;
+    }
+    // rng tables
+    e = dupload(c, &p, s->pmj_samples, 64 * 4096 * 8); if (e) return e; e = set_global(c, "pmj_samples", p); if (e) return e;
+    e = dupload(c, &p, s->blue_noise, 16 * 128 * 128 * 2); if (e) return e; e = set_global(c, "blue_noise_textures", p); if (e) return e;
+    // lights
+    c->has_lights = s->light_mesh_count > 0 && s->lights_total_weight > 0.0f;
+    e = set_global(c, "lights_total_weight", c->has_lights ? s->lights_total_weight : 0.0f); if (e) return e;
+    if (c->has_lights) {
+        e = dupload(c, &p, s->light_triangle_indices, (size_t)s->light_triangle_count * 4); if (e) return e; e = set_global(c, "light_triangle_indices", p); if (e) return e;
+        e = dupload(c, &p, s->light_triangle_cumulative_probability, (size_t)s->light_triangle_count * 4); if (e) return e; e = set_global(c, "light_triangle_cumulative_probability", p); if (e) return e;
+        e = set_global(c, "light_mesh_count", s->light_mesh_count); if (e) return e;
+        e = dupload(c, &p, s->light_mesh_cumulative_probability, (size_t)s->light_mesh_count * 4); if (e) return e; e = set_global(c, "light_mesh_cumulative_probability", p); if (e) return e;
+        e = dupload(c, &p, s->light_mesh_triangle_span, (size_t)s->light_mesh_count * 8); if (e) return e; e = set_global(c, "light_mesh_triangle_span", p); if (e) return e;
+        e = dupload(c, &p, s->light_mesh_transform_indices, (size_t)s->light_mesh_count * 4); if (e) return e; e = set_global(c, "light_mesh_transform_indices", p); if (e) return e;
+    }
+    // ray buffers (Pathtracer.h:5-119, Pathtracer.cpp:28-33,604-671)
+    DevTraceBuffer tb[2];
+    for (int i = 0; i < 2; i++) {
+        e |= alloc_soa(c, tb[i].origin, BATCH_SIZE); e |= alloc_soa(c, tb[i].direction, BATCH_SIZE); e |= dalloc(c, &tb[i].hits, (size_t)BATCH_SIZE * 16);
+        e |= dalloc(c, &tb[i].cone_angle, (size_t)BATCH_SIZE * 4); e |= dalloc(c, &tb[i].cone_width, (size_t)BATCH_SIZE * 4); e |= dalloc(c, &tb[i].medium, (size_t)BATCH_SIZE * 4);
+        e |= dalloc(c, &tb[i].pixel_index_and_flags, (size_t)BATCH_SIZE * 4); e |= alloc_soa(c, tb[i].throughput, BATCH_SIZE); e |= dalloc(c, &tb[i].last_pdf, (size_t)BATCH_SIZE * 4);
+        c->trace_hits[i] = tb[i].hits; c->trace_pix[i] = tb[i].pixel_index_and_flags;
+    }
+    if (e) return 1;
+    e = set_global(c, "ray_buffer_trace_0", tb[0]); if (e) return e;
+    e = set_global(c, "ray_buffer_trace_1", tb[1]); if (e) return e;
+    if (c->has_lights) {
+        DevShadowBuffer sb;
+        e |= alloc_soa(c, sb.origin, BATCH_SIZE); e |= alloc_soa(c, sb.direction, BATCH_SIZE); e |= dalloc(c, &sb.max_distance, (size_t)BATCH_SIZE * 4);
+        e |= dalloc(c, &sb.illumination_and_pixel_index, (size_t)BATCH_SIZE * 16);
+        if (e) return 1;
+        e = set_global(c, "ray_buffer_shadow", sb); if (e) return e;
+    }
+    int n_types = c->has_type[0] + c->has_type[1] + c->has_type[2] + c->has_type[3];
+    int n_buffers = (n_types + 1) / 2;
+    std::vector<DevMaterialBuffer> mbs((size_t)n_buffers);
+    for (auto& mb : mbs) {
+        e |= alloc_soa(c, mb.direction, BATCH_SIZE); e |= dalloc(c, &mb.hits, (size_t)BATCH_SIZE * 16); e |= dalloc(c, &mb.cone_angle, (size_t)BATCH_SIZE * 4);
+        e |= dalloc(c, &mb.cone_width, (size_t)BATCH_SIZE * 4); e |= dalloc(c, &mb.medium, (size_t)BATCH_SIZE * 4); e |= dalloc(c, &mb.pixel_index, (size_t)BATCH_SIZE * 4);
+        e |= alloc_soa(c, mb.throughput, BATCH_SIZE);
+    }
+    if (e) return 1;
+    CUdeviceptr d_mbs;
+    e = dupload(c, &d_mbs, mbs.data(), mbs.size() * sizeof(DevMaterialBuffer)); if (e) return e;
+    const char* mnames[4] = { "material_buffer_diffuse", "material_buffer_plastic", "material_buffer_dielectric", "material_buffer_conductor" };
+    int index = 0;
+    for (int m = 0; m < 4; m++) if (c->has_type[m]) {
+        uint64_t packed = (uint64_t)(d_mbs + (size_t)(index / 2) * sizeof(DevMaterialBuffer)) | (uint64_t)(index & 1);
+        e = set_global(c, mnames[m], packed); if (e) return e;
+        index++;
+    }
+    // AOVs + display surface
+    e = enable_aov(c, 0); if (e) return e;
+    e = push_aovs(c); if (e) return e;
+    e = make_array(&c->surf_array, c->pitch, c->height, 0, 4, CU_AD_FORMAT_FLOAT, true); if (e) return e;
+    e = make_surface(c->surf_array, &c->surf); if (e) return e;
+    e = set_global(c, "accumulator", c->surf); if (e) return e;
+    c->sizes.reset(c->pixel_count < BATCH_SIZE ? c->pixel_count : BATCH_SIZE);
+    e = set_global(c, "buffer_sizes", c->sizes); if (e) return e;
+    e = bake_luts(c); if (e) return e;
+    RCK(cuCtxSynchronize());
+    return 0;
+}
+
+static int svgf_init(ref_ctx* c) {   // Pathtracer.cpp:316-357
+    if (c->svgf_ready) return 0;
+    int e = 0;
+    const char* gnames[3] = { "gbuffer_normal_and_depth", "gbuffer_mesh_id_and_triangle_id", "gbuffer_screen_position_prev" };
+    int channels[3] = { 4, 2, 2 };
+    CUarray_format fmts[3] = { CU_AD_FORMAT_FLOAT, CU_AD_FORMAT_SIGNED_INT32, CU_AD_FORMAT_FLOAT };
+    for (int i = 0; i < 3; i++) {
+        CUarray arr; CUsurfObject s;
+        e = make_array(&arr, c->pitch, c->height, 0, channels[i], fmts[i], true); if (e) return e;
+        e = make_surface(arr, &s); if (e) return e;
+        e = set_global(c, gnames[i], s); if (e) return e;
+    }
+    e = enable_aov(c, 1) || enable_aov(c, 2) || enable_aov(c, 3); if (e) return e;
+    e = push_aovs(c); if (e) return e;
+    size_t px = (size_t)c->pitch * c->height;
+    CUdeviceptr p;
+    e = dalloc(c, &p, px * 16); if (e) return e; e = set_global(c, "frame_buffer_moment", p); if (e) return e;
+    const char* hn[5] = { "history_length", "history_direct", "history_indirect", "history_moment", "history_normal_and_depth" };
+    size_t hs[5] = { 4, 16, 16, 16, 16 };
+    for (int i = 0; i < 5; i++) { e = dalloc(c, &c->history_ptrs[i], px * hs[i]); if (e) return e; e = set_global(c, hn[i], c->history_ptrs[i]); if (e) return e; }
+    e = dalloc(c, &p, px * 16); if (e) return e; e = set_global(c, "taa_frame_prev", p); if (e) return e;
+    e = dalloc(c, &p, px * 16); if (e) return e; e = set_global(c, "taa_frame_curr", p); if (e) return e;
+    c->svgf_ready = true;
+    return 0;
+}
+
+int ref_set_config(ref_ctx* c, const ptb_config* cfg) {
+    RCK(cuCtxSetCurrent(c->cu));
+    c->config = *cfg;
+    c->config.aov_mask |= 1u;
+    int e = 0;
+    if (cfg->enable_svgf) { e = svgf_init(c); if (e) return e; c->config.aov_mask |= (1u << 1) | (1u << 2) | (1u << 3); }
+    for (int k = 0; k < 6; k++) if (c->config.aov_mask & (1u << k)) { e = enable_aov(c, k); if (e) return e; }
+    e = push_aovs(c); if (e) return e;
+    return set_global(c, "config", c->config);
+}
+
+int ref_set_camera(ref_ctx* c, const ptb_camera* cam, const float* vp, const float* vp_prev) {
+    RCK(cuCtxSetCurrent(c->cu));
+    int e = set_global(c, "camera", *cam); if (e) return e;
+    if (vp) {
+        struct { float a[16]; float b[16]; } data;
+        memcpy(data.a, vp, 64); memcpy(data.b, vp_prev ? vp_prev : vp, 64);
+        e = set_global(c, "svgf_data", data); if (e) return e;
+    }
+    return 0;
+}
+
+struct RefTimer {
+    ref_ctx* c; int stage; CUevent a = nullptr, b = nullptr;
+    static CUevent take(ref_ctx* c) { if (c->ev_used == c->events.size()) { CUevent e; cuEventCreate(&e, CU_EVENT_DEFAULT); c->events.push_back(e); } return c->events[c->ev_used++]; }
+    RefTimer(ref_ctx* c_, int s) : c(c_), stage(s) { if (c->timing) { a = take(c); b = take(c); cuEventRecord(a, nullptr); } }
+    ~RefTimer() { if (c->timing) { cuEventRecord(b, nullptr); c->timed.push_back({ stage, { a, b } }); } }
+};
+
+// Pathtracer::render() (Pathtracer.cpp:738-855).  Reads buffer_sizes back before every reset so ray counts are exact.
+int ref_render(ref_ctx* c, int sample_index) {
+    RCK(cuCtxSetCurrent(c->cu));
+    if (c->timing) { c->timed.clear(); c->ev_used = 0; }
+    CUdeviceptr d_sizes; size_t sz;
+    int e = get_global(c, "buffer_sizes", &d_sizes, &sz); if (e) return e;
+    int pixels_left = c->pixel_count;
+    int batch_size = c->pixel_count < BATCH_SIZE ? c->pixel_count : BATCH_SIZE;
+    auto harvest = [&]() -> int {
+        BufferSizes bs;
+        RCK(cuMemcpyDtoH(&bs, d_sizes, sizeof(bs)));
+        for (int b = 0; b < MAX_BOUNCES; b++) { c->total_trace[b] += bs.trace[b]; c->total_shadow[b] += bs.shadow[b];
+            c->total_shaded[0] += bs.diffuse[b]; c->total_shaded[1] += bs.plastic[b]; c->total_shaded[2] += bs.dielectric[b]; c->total_shaded[3] += bs.conductor[b]; }
+        return 0;
+    };
+    while (pixels_left > 0) {
+        int pixel_offset = c->pixel_count - pixels_left;
+        int pixel_count = batch_size < pixels_left ? batch_size : pixels_left;
+        { RefTimer t(c, 0); void* a[] = { &sample_index, &pixel_offset, &pixel_count }; e = launch(c, c->generate, a); if (e) return e; }
+        for (int bounce = 0; bounce < c->config.num_bounces; bounce++) {
+            { RefTimer t(c, 1); void* a[] = { &bounce }; e = launch(c, c->trace, a); if (e) return e; }
+            { RefTimer t(c, 2); void* a[] = { &bounce, &sample_index }; e = launch(c, c->sort, a); if (e) return e; }
+            { RefTimer t(c, 3);
+              for (int m = 0; m < 4; m++) if (c->has_type[m]) { void* a[] = { &bounce, &sample_index }; e = launch(c, c->material[m], a); if (e) return e; } }
+            if (c->has_lights && c->config.enable_next_event_estimation) { RefTimer t(c, 4); void* a[] = { &bounce }; e = launch(c, c->trace_shadow, a); if (e) return e; }
+        }
+        pixels_left -= batch_size;
+        if (pixels_left > 0) {
+            e = harvest(); if (e) return e;
+            c->sizes.reset(batch_size < pixels_left ? batch_size : pixels_left);
+            RCK(cuMemcpyHtoD(d_sizes, &c->sizes, sizeof(BufferSizes)));
+        }
+    }
+    {
+        RefTimer t(c, 5);
+        if (c->config.enable_svgf) {
+            { void* a[] = { &sample_index }; e = launch(c, c->svgf_reproject, a); if (e) return e; }
+            CUdeviceptr din = c->aov_fb[1], iin = c->aov_fb[2], dout = c->aov_acc[1], iout = c->aov_acc[2];
+            if (c->config.enable_spatial_variance) {
+                void* a[] = { &din, &iin, &dout, &iout }; e = launch(c, c->svgf_variance, a); if (e) return e;
+                std::swap(din, dout); std::swap(iin, iout);
+            }
+            for (int i = 0; i < c->config.num_atrous_iterations; i++) {
+                int step = 1 << i;
+                void* a[] = { &din, &iin, &dout, &iout, &step }; e = launch(c, c->svgf_atrous, a); if (e) return e;
+                std::swap(din, dout); std::swap(iin, iout);
+            }
+            { void* a[] = { &din, &iin }; e = launch(c, c->svgf_finalize, a); if (e) return e; }
+            if (c->config.enable_taa) {
+                { void* a[] = { &sample_index }; e = launch(c, c->taa, a); if (e) return e; }
+                { e = launch(c, c->taa_finalize, nullptr); if (e) return e; }
+            }
+        } else {
+            float n = float(sample_index);
+            void* a[] = { &n }; e = launch(c, c->accumulate, a); if (e) return e;
+        }
+    }
+    e = harvest(); if (e) return e;   // also the host<->device sync point, like the reference's blocking reset copy
+    c->sizes.reset(batch_size);
+    RCK(cuMemcpyHtoD(d_sizes, &c->sizes, sizeof(BufferSizes)));
+    for (int k = 0; k < 6; k++) if (c->aov_fb[k]) RCK(cuMemsetD8Async(c->aov_fb[k], 0, (size_t)c->pitch * c->height * 16, nullptr));   // aovs_clear_to_zero
+    c->frames++;
+    return 0;
+}
+
+int ref_sync(ref_ctx* c) {
+    RCK(cuCtxSetCurrent(c->cu));
+    RCK(cuCtxSynchronize());
+    if (c->timing && !c->timed.empty()) {
+        for (int i = 0; i < 6; i++) c->stage_ms[i] = 0;
+        for (auto& t : c->timed) { float ms = 0; cuEventElapsedTime(&ms, t.second.first, t.second.second); c->stage_ms[t.first] += ms; }
+        c->timed.clear();
+    }
+    return 0;
+}
+int ref_set_timing(ref_ctx* c, int on) { c->timing = on != 0; return 0; }
+int ref_get_stage_ms(ref_ctx* c, float* ms, int n) { for (int i = 0; i < n && i < 6; i++) ms[i] = c->stage_ms[i]; return 0; }
+
+// aov_type >= 0: framebuffer/accumulator of that AOV; aov_type < 0: the display surface
+int ref_download(ref_ctx* c, int aov_type, int accumulated, float* dst) {
+    RCK(cuCtxSetCurrent(c->cu));
+    RCK(cuCtxSynchronize());
+    size_t bytes = (size_t)c->pitch * c->height * 16;
+    if (aov_type < 0) {
+        CUDA_MEMCPY2D cp; memset(&cp, 0, sizeof(cp));
+        cp.srcMemoryType = CU_MEMORYTYPE_ARRAY; cp.srcArray = c->surf_array; cp.dstMemoryType = CU_MEMORYTYPE_HOST; cp.dstHost = dst;
+        cp.dstPitch = (size_t)c->pitch * 16; cp.WidthInBytes = cp.dstPitch; cp.Height = c->height;
+        RCK(cuMemcpy2D(&cp));
+        return 0;
+    }
+    CUdeviceptr p = accumulated ? c->aov_acc[aov_type] : c->aov_fb[aov_type];
+    if (!p) return 1;
+    RCK(cuMemcpyDtoH(dst, p, bytes));
+    return 0;
+}
+
+// Primary hits of the LAST batch (bounce 0 buffer): n x (pixel_index, uint4 hit) pairs copied out raw.
+int ref_read_primary(ref_ctx* c, uint32_t* pixel_index_out, uint32_t* hits_out, int max_count) {
+    RCK(cuCtxSetCurrent(c->cu));
+    RCK(cuCtxSynchronize());
+    int n = max_count < BATCH_SIZE ? max_count : BATCH_SIZE;
+    RCK(cuMemcpyDtoH(pixel_index_out, c->trace_pix[0], (size_t)n * 4));
+    RCK(cuMemcpyDtoH(hits_out, c->trace_hits[0], (size_t)n * 16));
+    return 0;
+}
+
+int ref_get_ray_stats(ref_ctx* c, ptb_ray_stats* out, int reset) {
+    memcpy(out->trace, c->total_trace, sizeof(c->total_trace)); memcpy(out->shadow, c->total_shadow, sizeof(c->total_shadow));
+    memcpy(out->shaded, c->total_shaded, sizeof(c->total_shaded)); out->frames = c->frames;
+    if (reset) { memset(c->total_trace, 0, sizeof(c->total_trace)); memset(c->total_shadow, 0, sizeof(c->total_shadow)); memset(c->total_shaded, 0, sizeof(c->total_shaded)); c->frames = 0; }
+    return 0;
+}
+
+int ref_launch_geometry(ref_ctx* c, int* out8) {   // trace kernel grid/block/smem as chosen by the occupancy API (for the record)
+    out8[0] = c->trace.gy; out8[1] = c->trace.bx * c->trace.by; out8[2] = c->trace.smem;
+    out8[3] = c->trace_shadow.gy; out8[4] = c->trace_shadow.bx * c->trace_shadow.by; out8[5] = c->trace_shadow.smem;
+    out8[6] = c->accumulate.bx; out8[7] = c->accumulate.by;
+    return 0;
+}
+
+} // extern "C"
