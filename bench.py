@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+Metric : Mrays/s (and ms/frame) at 1920x1080, 8 spp, Sponza CWBVH, 4 bounces, NEE + MIS    (configs[1])
+Step   : ONE 8-spp frame = passes sample_index 0..8 through the wavefront pipeline (9 traced passes: exactly what the
+         reference's `-N 8` capture does, Src/Main.cpp:142 -- its accumulator overwrites pass 0, AOV.h:35-46).
+         rays = closest-hit + shadow rays of all 9 passes, read from the device counters (never estimated).
+value  : device-timed (CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks),
+         scene and queues resident in HBM.
+e2e    : the same frames through the host façade (`Pathtracer.update()/render()`) with HOST buffers: every step
+         uploads the per-frame inputs the reference uploads (TLAS nodes + per-instance tables + camera,
+         Integrator.cpp:399-481) from pinned host memory and reads the finished frame back to pinned host memory.
+N > 1  : one process per GPU (torchrun); the frame is sharded by interleaved row bands, every rank traces its rows, one
+         NCCL all-gather of the packed tile framebuffers per frame (inside the timed region).  Total work is fixed as N
+         grows -> "scaling": "strong".
+
+`--impl reference` times the reference's OWN CUDA kernels (oracle/_ref/pathtracer_ref.cubin, compiled unmodified from
+/root/reference) through oracle/ref_harness.cpp with the reference's launch recipe, on 1 GPU, same scene/config/metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PASSES_PER_STEP = 9          # sample_index 0..8
+WIDTH, HEIGHT, BOUNCES = 1920, 1080, 4
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def load_workload(args):
+    """Sponza blob staged from the reference data when present; otherwise a procedural Sponza-like atrium."""
+    from gpu_raytracer_b200 import scene
+    staged = os.path.join(ROOT, "data", "_staged", "sponza.npz")
+    if args.scene == "sponza" or (args.scene == "auto" and os.path.exists(staged)):
+        blob = scene.load_blob(staged)
+        name = "Data/Sponza 1920x1080 8spp CWBVH 4 bounces NEE+MIS (blob staged from the reference's scene.xml)"
+    else:
+        desc = scene.procedural_scene("atrium", seed=7, width=WIDTH, height=HEIGHT, detail=args.detail)
+        blob = scene.build_blob(desc, 8, WIDTH, HEIGHT)
+        name = f"procedural atrium ({blob['triangles'].shape[0]} tris) 1920x1080 8spp CWBVH 4 bounces NEE+MIS (reference data not staged)"
+    blob["num_bounces"] = BOUNCES
+    assert (int(blob["width"]), int(blob["height"])) == (WIDTH, HEIGHT)
+    return blob, name
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
+
+
+def algorithmic_bytes(trav):
+    """closest-hit = 24 R + 16 W + 80/node + 48/triangle + 48/instance transform per ray;
+    shadow = 28 R + 80/node + 48/triangle + 48/instance (+ 16 R + 64 RMW on a miss)."""
+    closest = trav["rays"][0] * (24 + 16) + 80 * trav["nodes"][0] + 48 * trav["triangles"][0] + 48 * trav["instance_transforms"][0]
+    shadow = trav["rays"][1] * 28 + 80 * trav["nodes"][1] + 48 * trav["triangles"][1] + 48 * trav["instance_transforms"][1] + trav["shadow_misses"] * (16 + 64)
+    return closest, shadow
+
+
+def cpu_baseline(blob, budget_s=12.0):
+    """The oracle port (CPU restatement, OpenMP over all host cores) on a bounded sample of the same workload:
+    as many 8-row bands of the 1080p frame, 1 pass, as fit the time budget."""
+    from oracle.oracle import Oracle
+    cores = os.cpu_count() or 1
+    o = Oracle(blob, num_bounces=BOUNCES, threads=cores)
+    rows_done, t_total, rays = 0, 0.0, 0
+    y = 0
+    step = 8
+    while t_total < budget_s and y + step <= o.height:
+        before = int(o.counters.sum())
+        t0 = time.perf_counter()
+        o.render_pass(1, rows=(y, y + step))
+        t_total += time.perf_counter() - t0
+        rays += int(o.counters.sum()) - before
+        rows_done += step
+        y += step * 9          # spread the sampled bands over the frame
+        if y + step > o.height and rows_done < 64:
+            y = (rows_done // step) % 9 * step + step
+    return dict(value=rays / t_total / 1e6, unit="Mrays/s", cores=cores, kind="port",
+                sample=f"{rows_done} rows x {o.width} px x 1 pass of the same frame ({rays} rays in {t_total:.1f} s), oracle/pt_oracle.c with OpenMP")
+
+
+def cpu_bvh_build(blob):
+    """Reference CPU path the north star keeps: SAH sweep + CWBVH conversion, one job per mesh on all host cores."""
+    from concurrent.futures import ThreadPoolExecutor
+    from gpu_raytracer_b200 import scene
+    first, count = np.asarray(blob["mesh_tri_first"]), np.asarray(blob["mesh_tri_count"])
+    ranges = sorted(set(zip(first.tolist(), count.tolist())))
+    tri = np.asarray(blob["triangles"])
+    soups = []
+    for f, c in ranges:
+        t = tri[f:f + c]
+        p0 = t[:, 0:3]; soups.append(np.ascontiguousarray(np.stack([p0, p0 + t[:, 3:6], p0 + t[:, 6:9]], 1), dtype=np.float32))
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as pool:
+        built = list(pool.map(lambda s: scene.build_blas(s, 8), soups))
+    dt = time.perf_counter() - t0
+    ntri = int(sum(s.shape[0] for s in soups))
+    return dict(seconds=dt, triangles=ntri, triangles_per_s=ntri / dt, meshes=len(soups), nodes=int(sum(b.node_count for b in built)), cores=cores)
+
+
+def run_reference(args, blob, workload):
+    """Reference arm: the reference's own kernels on GPU 0."""
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/pathtracer_ref.cubin not built (needs /root/reference at build time)"}))
+        return
+    import torch
+    from gpu_raytracer_b200 import pathtracer as pt
+    torch.cuda.set_device(0)
+    cfg = pt.default_config(num_bounces=BOUNCES)
+    r = ref.Reference(blob, config=cfg)
+    for _ in range(args.warmup):
+        for si in range(PASSES_PER_STEP):
+            r.render_pass(si)
+    r.sync(); r.ray_stats(reset=True)
+    host = np.empty((r.height, r.pitch, 4), dtype=np.float32)
+    sampler = ClockSampler(0); sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for si in range(PASSES_PER_STEP):
+            r.render_pass(si)
+    r.sync()
+    dt = time.perf_counter() - t0          # the harness launches on the NULL stream of its own context; wall clock brackets a full sync
+    clocks = sampler.stop()
+    st = r.ray_stats()
+    rays = int(st["trace"].sum() + st["shadow"].sum())
+    # e2e: + frame readback to host each step
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for si in range(PASSES_PER_STEP):
+            r.render_pass(si)
+        host[...] = r.get_display()
+    r.sync()
+    dt_e2e = time.perf_counter() - t0
+    value = rays / dt / 1e6
+    line = {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "passes_per_step": PASSES_PER_STEP, "l2": "working set (ray queues + AOVs > 400 MB per pass) exceeds the 126 MB L2",
+                       "reference_arm": "reference CUDA kernels (Pathtracer.cu compiled unmodified) driven by oracle/ref_harness.cpp, reference launch recipe",
+                       "launch_geometry": r.launch_geometry()},
+            "rays_per_step": rays // args.steps, "clocks": clocks, "gpu_launches": 0,
+            "e2e": {"value": rays / dt_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(host.nbytes)},
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 0, "kind": "reference-cuda", "sample": "full workload on 1 GPU (the reference has no CPU implementation of this path)"}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ptb", choices=["ptb", "reference"])
+    ap.add_argument("--scene", default="auto", choices=["auto", "sponza", "procedural"])
+    ap.add_argument("--detail", type=float, default=4.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--band-rows", type=int, default=8)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        blob, workload = load_workload(args)
+        run_reference(args, blob, workload)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gpu_raytracer_b200 import pathtracer as pt, tiles
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    blob, workload = load_workload(args)
+    cfg = pt.default_config(num_bounces=BOUNCES)
+    p = pt.Pathtracer(blob, device=local_rank, rank=rank, world=world, band_rows=args.band_rows, config=cfg)
+    stream = torch.cuda.ExternalStream(p.stream())
+    hbm_peak, peak_src = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    mx_rows = tiles.max_owned_rows(HEIGHT, world, args.band_rows)
+    packed = torch.zeros((mx_rows, p.screen_pitch, 4), dtype=torch.float32, device="cuda")
+    gathered = torch.empty((world, mx_rows, p.screen_pitch, 4), dtype=torch.float32, device="cuda") if world > 1 else None
+    frame = torch.empty((HEIGHT, p.screen_pitch, 4), dtype=torch.float32, device="cuda") if world > 1 else None
+    host_frame = torch.empty((HEIGHT, p.screen_pitch, 4), dtype=torch.float32).pin_memory()
+
+    def one_frame(gather=True):
+        p.invalidated_gpu_config = True           # new frame: sample_index restarts at 0 (Integrator.cpp:518-521)
+        for _ in range(PASSES_PER_STEP):
+            p.update(); p.render()
+        if world > 1 and gather:
+            with torch.cuda.stream(stream):
+                p.export_rows(packed.data_ptr(), pt.AOV_RADIANCE)
+                dist.all_gather_into_tensor(gathered, packed)
+                p.assemble_rows(gathered.data_ptr(), mx_rows, frame.data_ptr())
+
+    # ---- warm-up, then the roofline accounting pass (instrumented traversal; outside every timed region)
+    for _ in range(args.warmup):
+        one_frame()
+    p.sync()
+    trav = p.measure_traversal(1)
+    p.ray_stats(reset=True)
+
+    # ---- timed region: device time, max over ranks
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = p.launch_count()
+    p.set_timing(True)
+    stage_tot = {}
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record()
+    for _ in range(args.steps):
+        one_frame()
+    with torch.cuda.stream(stream):
+        ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    p.sync()
+    last_pass_stages = p.stage_ms()                  # stage device times of the LAST pass of the timed region (CUDA events per stage)
+    p.set_timing(False)
+    launches = p.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    st = p.ray_stats(reset=True)
+    rays_local = int(st["trace"].sum() + st["shadow"].sum())
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda"); r = torch.tensor([rays_local], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    ms_max, rays_total = float(t.item()), float(r.item())
+
+    # ---- per-kernel timing of the dominant kernel: every trace launch of one frame bracketed by CUDA events on its stream
+    p.set_timing(True)
+    trace_ms = shadow_ms = 0.0
+    n_trace_launch = n_shadow_launch = 0
+    p.invalidated_gpu_config = True
+    for _ in range(PASSES_PER_STEP):
+        p.update(); p.render(); p.sync()
+        sm = p.stage_ms()
+        trace_ms += sm["trace"]; shadow_ms += sm["shadow_trace"]
+        n_trace_launch += BOUNCES; n_shadow_launch += BOUNCES
+    p.set_timing(False)
+    st_one = p.ray_stats(reset=True)
+    closest_bytes, shadow_bytes = algorithmic_bytes(trav)
+    # trav is one pass; scale node/triangle work to the 9 passes of a frame by the measured ray ratio of that frame
+    scale_c = float(st_one["trace"].sum()) / max(trav["rays"][0], 1)
+    ach_gbs = closest_bytes * scale_c / (trace_ms * 1e-3) / 1e9
+    roofline = {"kernel": "k_trace8<closest-hit>", "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "traffic": None,
+                "avg_launch_ms": trace_ms / n_trace_launch, "launches_timed": n_trace_launch,
+                "algorithmic_bytes_per_ray": closest_bytes / max(trav["rays"][0], 1),
+                "nodes_per_ray": trav["nodes"][0] / max(trav["rays"][0], 1), "triangles_per_ray": trav["triangles"][0] / max(trav["rays"][0], 1),
+                "shadow_kernel": {"achieved": shadow_bytes * (float(st_one["shadow"].sum()) / max(trav["rays"][1], 1)) / (max(shadow_ms, 1e-9) * 1e-3) / 1e9,
+                                  "algorithmic_bytes_per_ray": shadow_bytes / max(trav["rays"][1], 1)},
+                "whole_pipeline_algorithmic_gbs": None}
+
+    # ---- e2e: host buffers in, host frame out, every step
+    tl_nodes = np.ascontiguousarray(np.asarray(blob["bvh_nodes"])[: int(blob["tlas_node_count"]) * 80])
+    inst = [np.ascontiguousarray(blob[k]) for k in ("mesh_bvh_root_indices", "mesh_material_ids", "mesh_transforms", "mesh_transforms_inv", "mesh_transforms_prev")]
+    pinned = [torch.from_numpy(a.copy()).pin_memory() for a in [tl_nodes] + inst]
+    h2d = int(sum(a.numel() * a.element_size() for a in pinned)) + 60 + 44
+    import ctypes
+    lib = pt.lib()
+
+    def e2e_frame():
+        lib.ptb_update_instances(p._ctx, ctypes.c_void_p(pinned[0].data_ptr()), int(blob["tlas_node_count"]), int(inst[0].size),
+                                 *[ctypes.c_void_p(x.data_ptr()) for x in pinned[1:]])
+        p.invalidated_camera = True
+        one_frame()
+        src = frame if world > 1 else None
+        with torch.cuda.stream(stream):
+            if src is not None:
+                if rank == 0:
+                    host_frame.copy_(src, non_blocking=True)
+            else:
+                ptr, _ = p.display_device_ptr()
+                lib_rt.cudaMemcpyAsync(ctypes.c_void_p(host_frame.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(host_frame.numel() * 4), 2, ctypes.c_void_p(p.stream()))
+        p.sync()
+
+    lib_rt = ctypes.CDLL(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart.so.12")) if os.path.exists(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart.so.12")) else ctypes.CDLL("libcudart.so")
+    e2e_frame()
+    p.ray_stats(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        ev0.record()
+    for _ in range(args.steps):
+        e2e_frame()
+    with torch.cuda.stream(stream):
+        ev1.record()
+    barrier()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max(ev0.elapsed_time(ev1), 0.0)
+    st2 = p.ray_stats(reset=True)
+    t = torch.tensor([max(ms_e2e, wall_e2e)], dtype=torch.float64, device="cuda"); r2 = torch.tensor([float(st2["trace"].sum() + st2["shadow"].sum())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(r2, op=dist.ReduceOp.SUM)
+    e2e_val = float(r2.item()) / (float(t.item()) * 1e-3) / 1e6
+
+    if rank == 0:
+        value = rays_total / (ms_max * 1e-3) / 1e6
+        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "passes_per_step": PASSES_PER_STEP, "parallelism": f"tiles{world}x(bands of {args.band_rows} rows)" if world > 1 else "1 GPU",
+                           "l2": "working set (ray queues + AOVs > 400 MB per pass) exceeds the 126 MB L2", "rng_tables": blob.get("rng_source", "?"),
+                           "ms_per_frame": ms_max / args.steps},
+                "rays_per_step": int(rays_total / args.steps), "clocks": clocks, "gpu_launches": int(launches),
+                "stage_ms_last_pass": last_pass_stages,
+                "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(host_frame.numel() * 4), "ms_per_step": float(t.item()) / args.steps},
+                "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(blob)
+            line["cpu_bvh_build"] = cpu_bvh_build(blob)
+        print(json.dumps(line))
+    p.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -13,6 +13,7 @@
 #include "ptb.h"
 #include "ptb_kernels.cuh"
 #include "ptb_post.cuh"
+#include "ptb_svgf.cuh"
 
 #define CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx_fail(ctx, #expr, (int)e__); return (int)e__; } } while (0)
 #define CKD(expr) do { CUresult r__ = (expr); if (r__ != CUDA_SUCCESS) { ctx_fail(ctx, #expr, 1000 + (int)r__); return 1000 + (int)r__; } } while (0)
@@ -69,6 +70,7 @@ struct ptb_ctx {
     bool luts_ready = false;
     uint4* tap_hits = nullptr;
     long long launches = 0;
+    bool stats_mode = false;
     bool timing = false;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;
     std::vector<cudaEvent_t> event_pool;
@@ -151,7 +153,8 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     }
     if (dev_alloc(ctx, &F.sq.od0, N) || dev_alloc(ctx, &F.sq.od1, N) || dev_alloc(ctx, &F.sq.illum, N)) { ptb_destroy(ctx); return PTB_E_STATE; }
     for (int m = 0; m < 4; m++) if (dev_alloc(ctx, &F.matq[m], N)) { ptb_destroy(ctx); return PTB_E_STATE; }
-    if (dev_alloc(ctx, &F.counters, 1) || dev_alloc(ctx, &F.totals, 1)) { ptb_destroy(ctx); return PTB_E_STATE; }
+    if (dev_alloc(ctx, &F.counters, 1) || dev_alloc(ctx, &F.totals, 1) || dev_alloc(ctx, &F.trace_stats, 2)) { ptb_destroy(ctx); return PTB_E_STATE; }
+    CK(cudaMemsetAsync(F.trace_stats, 0, 2 * sizeof(TraceStats), ctx->stream));
     CK(cudaMemsetAsync(F.counters, 0, sizeof(Counters), ctx->stream));
     CK(cudaMemsetAsync(F.totals, 0, sizeof(RayTotals), ctx->stream));
     const size_t pixels = (size_t)F.pitch * F.height;
@@ -162,8 +165,10 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     CK(cudaMemsetAsync(F.aov[PTB_AOV_RADIANCE].fb, 0, pixels * sizeof(float4), ctx->stream));
     CK(cudaMemsetAsync(F.aov[PTB_AOV_RADIANCE].acc, 0, pixels * sizeof(float4), ctx->stream));
 
-    CK(cudaFuncSetAttribute(k_trace8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CK(cudaFuncSetAttribute(k_trace8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_trace8<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_trace8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_trace8<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_trace8<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CK(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return 0;
@@ -453,7 +458,8 @@ extern "C" int ptb_render(ptb_ctx* ctx, int sample_index) {
     { StageTimer t(ctx, ST_GENERATE); k_generate<<<g1d, 256, 0, st>>>(F, sample_index); ctx->launches++; }
     for (int bounce = 0; bounce < F.config.num_bounces; bounce++) {
         { StageTimer t(ctx, ST_TRACE);
-          if (ctx->bvh_kind == 8) k_trace8<false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce);
+          if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<false, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce);
+                                    else                 k_trace8<false, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce); }
           else                    k_trace2<false><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
           ctx->launches++; }
         { StageTimer t(ctx, ST_SORT); k_sort<<<g1d, 256, 0, st>>>(F, bounce, sample_index); ctx->launches++; }
@@ -464,7 +470,8 @@ extern "C" int ptb_render(ptb_ctx* ctx, int sample_index) {
           if (ctx->has_type[3]) { k_shade<BSDFConductor><<<g1d, 256, 0, st>>>(F, bounce, sample_index); ctx->launches++; } }
         if (nee) {
             StageTimer t(ctx, ST_SHADOW);
-            if (ctx->bvh_kind == 8) k_trace8<true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce);
+            if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<true, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce);
+                                      else                 k_trace8<true, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce); }
             else                    k_trace2<true><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
             ctx->launches++;
         }
@@ -480,6 +487,24 @@ extern "C" int ptb_render(ptb_ctx* ctx, int sample_index) {
     CK(cudaGetLastError());
     ctx->last_sample_index = sample_index;
     ctx->frames_since_reset++;
+    return 0;
+}
+
+extern "C" int ptb_measure_traversal(ptb_ctx* ctx, int sample_index, ptb_traversal_stats* out) {
+    if (!ctx || !out) return PTB_E_BADARG;
+    if (!ctx->has_scene) return PTB_E_NOSCENE;
+    if (ctx->bvh_kind != 8) return PTB_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->F.trace_stats, 0, 2 * sizeof(TraceStats), ctx->stream));
+    ctx->stats_mode = true;
+    int e = ptb_render(ctx, sample_index);
+    ctx->stats_mode = false;
+    if (e) return e;
+    TraceStats h[2];
+    CK(cudaMemcpyAsync(h, ctx->F.trace_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 2; k++) { out->rays[k] = h[k].rays; out->nodes[k] = h[k].nodes; out->triangles[k] = h[k].triangles; out->instance_transforms[k] = h[k].instance_transforms; }
+    out->shadow_misses = h[1].misses;
     return 0;
 }
 

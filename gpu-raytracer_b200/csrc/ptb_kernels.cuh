@@ -80,7 +80,9 @@ PTB_DI uint2 stack_pop(const TraceShared& S, const uint2* local, int& sp) {
     return sp < PTB_SM_STACK ? S.stack[sp * PTB_TRACE_BLOCK + threadIdx.x] : local[sp - PTB_SM_STACK];
 }
 
-template <bool SHADOW>
+// STATS = true additionally counts node visits / triangle tests / instance transforms per ray kind (roofline accounting:
+// algorithmic bytes = 80 B per node + 48 B per triangle + 48 B per instance transform + the ray/hit streams).
+template <bool SHADOW, bool STATS>
 __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace8(const __grid_constant__ Frame P, int bounce) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
     Hit hit; hit.t = 0.0f; hit.u = hit.v = 0.0f; hit.mesh_id = 0; hit.triangle_id = PTB_INVALID;   // shadow rays: hit.t = max distance
     int tlas_sp = PTB_INVALID, mesh_id = 0;
     bool identity = true, live = false, exhausted = false;
+    unsigned long long st_nodes = 0, st_tris = 0, st_xf = 0, st_rays = 0, st_miss = 0;
 
     while (true) {
         // ---- refill idle lanes (one atomic per warp)
@@ -125,10 +128,24 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                     oct4 = ray_octant_inv4(ray.d);
                     cur = make_uint2(0u, 0x80000000u);
                     sp = 0; tlas_sp = PTB_INVALID; live = true;
+                    if (STATS) st_rays++;
                 } else exhausted = true;
             }
         }
-        if (__ballot_sync(FULL, live) == 0) return;   // nothing in flight and the queue is empty
+        if (__ballot_sync(FULL, live) == 0) {          // nothing in flight and the queue is empty
+            if (STATS) {
+                for (int o = 16; o > 0; o >>= 1) {
+                    st_nodes += __shfl_down_sync(FULL, st_nodes, o); st_tris += __shfl_down_sync(FULL, st_tris, o);
+                    st_xf += __shfl_down_sync(FULL, st_xf, o); st_rays += __shfl_down_sync(FULL, st_rays, o); st_miss += __shfl_down_sync(FULL, st_miss, o);
+                }
+                if (lane == 0) {
+                    TraceStats* ts = P.trace_stats + (SHADOW ? 1 : 0);
+                    atomicAdd(&ts->nodes, st_nodes); atomicAdd(&ts->triangles, st_tris); atomicAdd(&ts->instance_transforms, st_xf);
+                    atomicAdd(&ts->rays, st_rays); atomicAdd(&ts->misses, st_miss);
+                }
+            }
+            return;
+        }
 
         int lost = 0;
         while (true) {
@@ -151,6 +168,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                         const float4* n = P.nodes8 + 5 * size_t(ni);
                         n0 = __ldg(n); n1 = __ldg(n + 1); n2 = __ldg(n + 2); n3 = __ldg(n + 3); n4 = __ldg(n + 4);
                     }
+                    if (STATS) st_nodes++;
                     unsigned hm = cwbvh_node_intersect(ray, oct4, hit.t, n0, n1, n2, n3, n4);
                     unsigned imask = byte_of(__float_as_uint(n0.w), 3);
                     cur.x = __float_as_uint(n1.x);
@@ -178,6 +196,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                     ray.o = xform_pos(inv, ray.o);
                     ray.d = xform_dir(inv, ray.d);
                     oct4 = ray_octant_inv4(ray.d);
+                    if (STATS) st_xf++;
                 }
                 cur = make_uint2(root & 0x7fffffffu, 0x80000000u);
                 tri.y = 0;
@@ -195,6 +214,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                 if (want) {
                     unsigned ti = msb(tri.y);
                     tri.y &= ~(1u << ti);
+                    if (STATS) st_tris++;
                     if (SHADOW) {
                         if (occludes_triangle(P, int(tri.x + ti), ray, hit.t)) { terminated = true; tri.y = 0; }
                     } else {
@@ -209,6 +229,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                     if (sp == 0) {
                         if (SHADOW) {
                             // unoccluded: deposit the light sample (Pathtracer.cu:183-196)
+                            if (STATS) st_miss++;
                             float4 ill = P.sq.illum[ray_index];
                             int px = __float_as_int(P.sq.od1[ray_index].w);
                             float4 v = make_float4(ill.x, ill.y, ill.z, 0.0f);
@@ -804,7 +825,10 @@ __global__ void __launch_bounds__(256, 2) k_shade(const __grid_constant__ Frame 
             const int index = queue[i];
             float4 a = q.od0[index], b = q.od1[index];
             float3 ray_direction = f3(a.w, b.x, b.y);
-            Hit hit = unpack_hit(__ldg(q.hit + index));
+            // The reference copies the hit from the trace buffer into the material buffer (kernel_sort) and so packs the
+            // barycentrics to 16 bits a SECOND time (HitBuffer::set after HitBuffer::get, Buffers.h:28-47); that round trip is
+            // not the identity (int(q / 65535.0f * 65535.0f) can be q - 1).  We compact by index, so replay it here.
+            Hit hit = unpack_hit(pack_hit(unpack_hit(__ldg(q.hit + index))));
             unsigned pf = q.pix[index];
             int pixel_index = int(pf & ~PTB_FLAGS_ALL);
             int medium_id = (pf & PTB_FLAG_INSIDE_MEDIUM) ? q.medium[index] : PTB_INVALID;

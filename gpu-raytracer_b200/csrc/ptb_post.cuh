@@ -1,4 +1,4 @@
-// Init-time Kulla-Conty LUT baking (KullaConty.h:83-240) and the SVGF / TAA post passes (SVGF.h, TAA.h).
+// Init-time Kulla-Conty LUT baking (KullaConty.h:83-240).
 #pragma once
 #include "ptb_device.cuh"
 
@@ -101,11 +101,3 @@ __global__ void k_average_conductor(const float* dir, float* out) {
     out[tid] = 2.0f * avg;
 }
 
-// ------------------------------------------------------------------------------------------ SVGF + TAA
-// (implemented in ptb_svgf.cuh once the path-tracing core is parity-green; until then asking for SVGF is an error,
-//  never a silent fallback)
-static int launch_svgf(Frame& F, cudaStream_t st, int sample_index, int grid, long long* launches) {
-    (void)F; (void)st; (void)sample_index; (void)grid; (void)launches;
-    fprintf(stderr, "[ptb] SVGF/TAA passes are not built yet\n");
-    return PTB_E_STATE;
-}

@@ -1,0 +1,339 @@
+// SVGF (temporal reprojection, spatial variance, a-trous wavelet filter, finalize) and TAA post passes.
+// Reference: Src/CUDA/SVGF/SVGF.h:100-609, Src/CUDA/SVGF/TAA.h:10-172.  The g-buffers are plain pitch-linear
+// HBM arrays (the reference uses CUDA surfaces bound to arrays); reads past the edge clamp like cudaBoundaryModeClamp.
+// All kernels are 1-D grid-stride over the pitch x height pixel grid, rows contiguous -> coalesced 128-bit accesses.
+#pragma once
+#include "ptb_kernels.cuh"
+
+#define PTB_SVGF_EPS 1e-8f
+#define PTB_FEEDBACK_ITERATION 1
+
+PTB_DI float4 gbuf_nd(const Frame& P, int x, int y) {
+    x = min(max(x, 0), P.pitch - 1); y = min(max(y, 0), P.height - 1);
+    return P.svgf.gbuf_normal_depth[x + y * P.pitch];
+}
+PTB_DI float4 lerp4(float4 a, float4 b, float t) { return (1.0f - t) * a + t * b; }
+PTB_DI float3 lerp3(float3 a, float3 b, float t) { return (1.0f - t) * a + t * b; }
+
+PTB_DI bool tap_consistent(const Frame& P, int x, int y, float3 normal, float depth) {
+    if (x < 0 || x >= P.width) return false;
+    if (y < 0 || y >= P.height) return false;
+    float4 prev = P.svgf.history_normal_depth[x + y * P.pitch];
+    float3 pn = oct_decode_normal(f2(prev.x, prev.y));
+    return dot(normal, pn) > 0.95f && fabsf(depth - prev.z) < 2.0f;
+}
+
+PTB_DI float2 edge_stopping_weights(const Frame& P, int dx, int dy, float2 cgrad, float cdepth, float depth, float3 cn, float3 n,
+                                    float cl_d, float cl_i, float l_d, float l_i, float denom_d, float denom_i) {
+    float d = cgrad.x * float(dx) + cgrad.y * float(dy);
+    float ln_w_z = fabsf(cdepth - depth) / (P.config.sigma_z * fabsf(d) + PTB_SVGF_EPS);
+    float w_n = powf(fmaxf(0.0f, dot(cn, n)), P.config.sigma_n);
+    float w_d = w_n * expf(-fabsf(cl_d - l_d) * denom_d - ln_w_z);
+    float w_i = w_n * expf(-fabsf(cl_i - l_i) * denom_i - ln_w_z);
+    return f2(w_d, w_i);
+}
+
+__global__ void __launch_bounds__(256) k_svgf_reproject(const __grid_constant__ Frame P, int sample_index) {
+    const int total = P.width * P.height;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int y = i / P.width, x = i - y * P.width;
+        int px = x + y * P.pitch;
+        float4 direct = P.aov[PTB_AOV_RADIANCE_DIRECT].fb[px];
+        float4 indirect = P.aov[PTB_AOV_RADIANCE_INDIRECT].fb[px];
+        float4 moment;
+        moment.x = luminance(direct.x, direct.y, direct.z);
+        moment.y = luminance(indirect.x, indirect.y, indirect.z);
+        moment.z = moment.x * moment.x;
+        moment.w = moment.y * moment.y;
+        float4 nd = P.svgf.gbuf_normal_depth[px];
+        float2 sprev = P.svgf.gbuf_screen_prev[px];
+        float3 normal = oct_decode_normal(f2(nd.x, nd.y));
+        float depth = nd.z, depth_prev = nd.w;
+        if (depth == 0.0f) continue;                      // sky pixel
+        float u_prev = 0.5f + 0.5f * sprev.x, v_prev = 0.5f + 0.5f * sprev.y;
+        float s_prev = u_prev * float(P.width), t_prev = v_prev * float(P.height);
+        int x_prev = int(s_prev - 0.5f), y_prev = int(t_prev - 0.5f);
+        float fs = s_prev - floorf(s_prev), ft = t_prev - floorf(t_prev);
+        float ofs = 1.0f - fs, oft = 1.0f - ft;
+        float w0 = ofs * oft, w1 = fs * oft, w2 = ofs * ft;
+        float w3 = 1.0f - w0 - w1 - w2;
+        float weights[4] = { w0, w1, w2, w3 };
+        float wsum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                int tap = k + j * 2;
+                if (tap_consistent(P, x_prev + k, y_prev + j, normal, depth_prev)) wsum += weights[tap]; else weights[tap] = 0.0f;
+            }
+        float4 pd = f4(0.0f), pi = f4(0.0f), pm = f4(0.0f);
+        if (wsum > 0.0f) {
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    int tap = k + j * 2;
+                    if (weights[tap] != 0.0f) {
+                        int ti = (x_prev + k) + (y_prev + j) * P.pitch;
+                        pd += weights[tap] * P.svgf.history_direct[ti];
+                        pi += weights[tap] * P.svgf.history_indirect[ti];
+                        pm += weights[tap] * P.svgf.history_moment[ti];
+                    }
+                }
+        } else {
+            for (int j = -1; j <= 1; j++)
+                for (int k = -1; k <= 1; k++) {
+                    int tx = x_prev + k, ty = y_prev + j;
+                    if (tap_consistent(P, tx, ty, normal, depth_prev)) {
+                        int ti = tx + ty * P.pitch;
+                        pd += P.svgf.history_direct[ti]; pi += P.svgf.history_indirect[ti]; pm += P.svgf.history_moment[ti];
+                        wsum += 1.0f;
+                    }
+                }
+        }
+        if (wsum > 0.0f) {
+            pd = pd / wsum; pi = pi / wsum; pm = pm / wsum;
+            int history = ++P.svgf.history_length[px];
+            float inv_history = 1.0f / float(history);
+            float a_c = fmaxf(P.config.alpha_colour, inv_history);
+            float a_m = fmaxf(P.config.alpha_moment, inv_history);
+            direct = lerp4(pd, direct, a_c);
+            indirect = lerp4(pi, indirect, a_c);
+            moment = lerp4(pm, moment, a_m);
+            if (history >= 4 || !P.config.enable_spatial_variance) {
+                direct.w = fmaxf(0.0f, moment.z - moment.x * moment.x);
+                indirect.w = fmaxf(0.0f, moment.w - moment.y * moment.y);
+            }
+        } else {
+            P.svgf.history_length[px] = 0;
+            direct.w = 1.0f; indirect.w = 1.0f;
+        }
+        P.aov[PTB_AOV_RADIANCE_DIRECT].fb[px] = direct;
+        P.aov[PTB_AOV_RADIANCE_INDIRECT].fb[px] = indirect;
+        P.svgf.moment[px] = moment;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_svgf_variance(const __grid_constant__ Frame P, const float4* din, const float4* iin, float4* dout, float4* iout) {
+    const int total = P.pitch * P.height;                 // the reference runs this one over the padded pitch (SVGF.h:293)
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int y = idx / P.pitch, x = idx - y * P.pitch;
+        int px = idx;
+        int history = P.svgf.history_length[px];
+        float4 cd = din[px], ci = iin[px];
+        if (history >= 4) { dout[px] = cd; iout[px] = ci; continue; }
+        float ldenom = 1.0f / P.config.sigma_l;
+        float cl_d = luminance(cd.x, cd.y, cd.z), cl_i = luminance(ci.x, ci.y, ci.z);
+        float4 cnd = gbuf_nd(P, x, y);
+        float3 cn = oct_decode_normal(f2(cnd.x, cnd.y));
+        float cdepth = cnd.z;
+        float2 cgrad = f2(gbuf_nd(P, x + 1, y).z - cdepth, gbuf_nd(P, x, y + 1).z - cdepth);
+        if (cdepth == 0.0f) { dout[px] = cd; iout[px] = ci; continue; }
+        float sw_d = 1.0f, sw_i = 1.0f;
+        float4 sc_d = cd, sc_i = ci, sm = f4(0.0f);
+        for (int j = -3; j <= 3; j++) {
+            int ty = y + j;
+            if (ty < 0 || ty >= P.height) continue;
+            for (int k = -3; k <= 3; k++) {
+                int tx = x + k;
+                if (tx < 0 || tx >= P.width) continue;
+                if (k == 0 && j == 0) continue;
+                int ti = tx + ty * P.pitch;
+                float4 td = din[ti], tind = iin[ti], tm = P.svgf.moment[ti];
+                float l_d = luminance(td.x, td.y, td.z), l_i = luminance(tind.x, tind.y, tind.z);
+                float4 tnd = P.svgf.gbuf_normal_depth[ti];
+                float3 n = oct_decode_normal(f2(tnd.x, tnd.y));
+                float2 w = edge_stopping_weights(P, k, j, cgrad, cdepth, tnd.z, cn, n, cl_d, cl_i, l_d, l_i, ldenom, ldenom);
+                sw_d += w.x; sw_i += w.y;
+                sc_d += w.x * td; sc_i += w.y * tind;
+                sm += tm * make_float4(w.x, w.y, w.x, w.y);
+            }
+        }
+        sw_d = fmaxf(sw_d, 1e-6f); sw_i = fmaxf(sw_i, 1e-6f);
+        sc_d = sc_d / sw_d; sc_i = sc_i / sw_i;
+        sm = make_float4(sm.x / sw_d, sm.y / sw_i, sm.z / sw_d, sm.w / sw_i);
+        sc_d.w = fmaxf(0.0f, sm.z - sm.x * sm.x);
+        sc_i.w = fmaxf(0.0f, sm.w - sm.y * sm.y);
+        dout[px] = sc_d; iout[px] = sc_i;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_svgf_atrous(const __grid_constant__ Frame P, const float4* din, const float4* iin, float4* dout, float4* iout, int step) {
+    const int total = P.width * P.height;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int y = i / P.width, x = i - y * P.width;
+        int px = x + y * P.pitch;
+        float vb_d = 0.0f, vb_i = 0.0f;
+#pragma unroll
+        for (int j = -1; j <= 1; j++) {
+            int ty = min(max(y + j, 0), P.height - 1);
+#pragma unroll
+            for (int k = -1; k <= 1; k++) {
+                int tx = min(max(x + k, 0), P.width - 1);
+                float v_d = din[tx + ty * P.pitch].w, v_i = iin[tx + ty * P.pitch].w;
+                float kw = scalbnf(0.25f, -(abs(k) + abs(j)));
+                vb_d += v_d * kw; vb_i += v_i * kw;
+            }
+        }
+        float denom_d = rsqrtf(P.config.sigma_l * P.config.sigma_l * fmaxf(0.0f, vb_d) + PTB_SVGF_EPS);
+        float denom_i = rsqrtf(P.config.sigma_l * P.config.sigma_l * fmaxf(0.0f, vb_i) + PTB_SVGF_EPS);
+        float4 cd = din[px], ci = iin[px];
+        float cl_d = luminance(cd.x, cd.y, cd.z), cl_i = luminance(ci.x, ci.y, ci.z);
+        float4 cnd = P.svgf.gbuf_normal_depth[px];
+        float3 cn = oct_decode_normal(f2(cnd.x, cnd.y));
+        float cdepth = cnd.z;
+        if (cdepth == 0.0f) continue;
+        float2 cgrad = f2(gbuf_nd(P, x + 1, y).z - cdepth, gbuf_nd(P, x, y + 1).z - cdepth);
+        float sw_d = 1.0f, sw_i = 1.0f;
+        float4 sc_d = cd, sc_i = ci;
+#pragma unroll
+        for (int j = -1; j <= 1; j++) {
+            int ty = y + j * step;
+            if (ty < 0 || ty >= P.height) continue;
+#pragma unroll
+            for (int k = -1; k <= 1; k++) {
+                int tx = x + k * step;
+                if (tx < 0 || tx >= P.width) continue;
+                if (k == 0 && j == 0) continue;
+                int ti = tx + ty * P.pitch;
+                float4 td = din[ti], tind = iin[ti];
+                float l_d = luminance(td.x, td.y, td.z), l_i = luminance(tind.x, tind.y, tind.z);
+                float4 tnd = P.svgf.gbuf_normal_depth[ti];
+                float3 n = oct_decode_normal(f2(tnd.x, tnd.y));
+                float2 w = edge_stopping_weights(P, k * step, j * step, cgrad, cdepth, tnd.z, cn, n, cl_d, cl_i, l_d, l_i, denom_d, denom_i);
+                sw_d += w.x; sw_i += w.y;
+                sc_d += make_float4(w.x, w.x, w.x, w.x * w.x) * td;
+                sc_i += make_float4(w.y, w.y, w.y, w.y * w.y) * tind;
+            }
+        }
+        float inv_d = 1.0f / sw_d, inv_i = 1.0f / sw_i;
+        sc_d = sc_d * inv_d; sc_i = sc_i * inv_i;
+        sc_d.w *= inv_d; sc_i.w *= inv_i;
+        dout[px] = sc_d; iout[px] = sc_i;
+        if (step == (1 << PTB_FEEDBACK_ITERATION)) { P.svgf.history_direct[px] = sc_d; P.svgf.history_indirect[px] = sc_i; }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_svgf_finalize(const __grid_constant__ Frame P, const float4* cdirect, const float4* cindirect) {
+    const int total = P.width * P.height;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int y = i / P.width, x = i - y * P.width;
+        int px = x + y * P.pitch;
+        float4 direct = cdirect[px], indirect = cindirect[px];
+        float4 colour = (direct + indirect) * P.aov[PTB_AOV_ALBEDO].fb[px];
+        P.display[px] = colour;
+        if (P.config.enable_taa) {
+            colour = colour / (1.0f + luminance(colour.x, colour.y, colour.z));
+            colour.x = safe_sqrt(colour.x); colour.y = safe_sqrt(colour.y); colour.z = safe_sqrt(colour.z);
+            P.svgf.taa_curr[px] = colour;
+        }
+        float4 moment = P.svgf.moment[px];
+        float4 nd = P.svgf.gbuf_normal_depth[px];
+        if (P.config.num_atrous_iterations <= PTB_FEEDBACK_ITERATION) { P.svgf.history_direct[px] = direct; P.svgf.history_indirect[px] = indirect; }
+        P.svgf.history_moment[px] = moment;
+        P.svgf.history_normal_depth[px] = nd;
+        P.svgf.gbuf_normal_depth[px] = f4(0.0f);
+        P.svgf.gbuf_ids[px] = make_int2(0, 0);
+        if (!P.config.enable_taa) P.svgf.gbuf_screen_prev[px] = f2(0.0f, 0.0f);
+    }
+}
+
+PTB_DI float mitchell_netravali(float x) {
+    const float B = 1.0f / 3.0f, C = 1.0f / 3.0f;
+    x = fabsf(x);
+    float x2 = x * x, x3 = x2 * x;
+    if (x < 1.0f) return (1.0f / 6.0f) * ((12.0f - 9.0f * B - 6.0f * C) * x3 + (-18.0f + 12.0f * B + 6.0f * C) * x2 + (6.0f - 2.0f * B));
+    if (x < 2.0f) return (1.0f / 6.0f) * ((-B - 6.0f * C) * x3 + (6.0f * B + 30.0f * C) * x2 + (-12.0f * B - 48.0f * C) * x + (8.0f * B + 24.0f * C));
+    return 0.0f;
+}
+PTB_DI float3 rgb_to_ycocg(float3 c) { return f3(0.25f * c.x + 0.5f * c.y + 0.25f * c.z, 0.5f * c.x - 0.5f * c.z, -0.25f * c.x + 0.5f * c.y - 0.25f * c.z); }
+PTB_DI float3 ycocg_to_rgb(float3 c) { return f3(__saturatef(c.x + c.y - c.z), __saturatef(c.x + c.z), __saturatef(c.x - c.y - c.z)); }
+PTB_DI float3 clamp3(float3 v, float3 a, float3 b) { return f3(clampf(v.x, a.x, b.x), clampf(v.y, a.y, b.y), clampf(v.z, a.z, b.z)); }
+
+__global__ void __launch_bounds__(256) k_taa(const __grid_constant__ Frame P, int sample_index) {
+    const int total = P.width * P.height;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int y = idx / P.width, x = idx - y * P.width;
+        int px = x + y * P.pitch;
+        const float4* curr = P.svgf.taa_curr;
+        float4 colour = curr[px];
+        if (sample_index == 0) { P.display[px] = colour; continue; }
+        float2 sprev = P.svgf.gbuf_screen_prev[px];
+        float u_prev = 0.5f + 0.5f * sprev.x, v_prev = 0.5f + 0.5f * sprev.y;
+        float s_prev = u_prev * float(P.width), t_prev = v_prev * float(P.height);
+        int x_prev = int(s_prev + 0.5f), y_prev = int(t_prev + 0.5f);
+        float sum_w = 0.0f; float4 sum = f4(0.0f);
+        for (int j = y_prev - 2; j < y_prev + 2; j++) {
+            if (j < 0 || j >= P.height) continue;
+            for (int i = x_prev - 2; i < x_prev + 2; i++) {
+                if (i < 0 || i >= P.width) continue;
+                float w = mitchell_netravali(float(i) + 0.5f - s_prev) * mitchell_netravali(float(j) + 0.5f - t_prev);
+                sum_w += w;
+                sum += w * P.svgf.taa_prev[i + j * P.pitch];
+            }
+        }
+        if (sum_w > 0.0f) {
+            float3 c_curr = rgb_to_ycocg(f3(colour));
+            float3 c_prev = rgb_to_ycocg(f3(sum / sum_w));
+            float3 avg = c_curr, var = c_curr * c_curr;
+            auto tap = [&](int off) { float3 f = rgb_to_ycocg(f3(curr[px + off])); avg += f; var += f * f; };
+            if (x >= 1) { if (y >= 1) tap(-P.pitch - 1); tap(-1); if (y < P.height - 1) tap(P.pitch - 1); }
+            if (y >= 1) tap(-P.pitch);
+            if (y < P.height - 1) tap(P.pitch);
+            if (x < P.width - 1) { if (y >= 1) tap(1 - P.pitch); tap(1); if (y < P.height - 1) tap(1 + P.pitch); }
+            avg *= 1.0f / 9.0f; var *= 1.0f / 9.0f;
+            float3 sigma2 = var - avg * avg;
+            float3 sigma = f3(safe_sqrt(sigma2.x), safe_sqrt(sigma2.y), safe_sqrt(sigma2.z));
+            float3 cmin = avg - 1.25f * sigma, cmax = avg + 1.25f * sigma;
+            c_prev = clamp3(c_prev, cmin, cmax);
+            float3 integrated = ycocg_to_rgb(lerp3(c_prev, c_curr, 0.1f));
+            colour.x = integrated.x; colour.y = integrated.y; colour.z = integrated.z;
+        }
+        P.display[px] = colour;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_taa_finalize(const __grid_constant__ Frame P) {
+    const int total = P.width * P.height;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int y = idx / P.width, x = idx - y * P.width;
+        int px = x + y * P.pitch;
+        float4 colour = P.display[px];
+        P.svgf.taa_prev[px] = colour;
+        colour = colour * colour;
+        colour = colour / (1.0f - luminance(colour.x, colour.y, colour.z));
+        P.display[px] = colour;
+        P.svgf.gbuf_screen_prev[px] = f2(0.0f, 0.0f);
+    }
+}
+
+// clears every enabled framebuffer after the SVGF passes (aovs_clear_to_zero, Integrator.cpp:377-383)
+__global__ void __launch_bounds__(256) k_clear_framebuffers(const __grid_constant__ Frame P) {
+    const int total = P.pitch * P.height;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+#pragma unroll
+        for (int k = 0; k < PTB_AOV_COUNT; k++) if (P.aov[k].fb) P.aov[k].fb[i] = f4(0.0f);
+}
+
+// launch sequence of the SVGF branch of Pathtracer::render (Pathtracer.cpp:798-837)
+static int launch_svgf(Frame& F, cudaStream_t st, int sample_index, int grid, long long* launches) {
+    if (F.world != 1) { fprintf(stderr, "[ptb] SVGF needs the whole frame on one GPU (stencil reach 63 px); gather the noisy AOVs first\n"); return PTB_E_STATE; }
+    k_svgf_reproject<<<grid, 256, 0, st>>>(F, sample_index); (*launches)++;
+    float4* din = F.aov[PTB_AOV_RADIANCE_DIRECT].fb; float4* iin = F.aov[PTB_AOV_RADIANCE_INDIRECT].fb;
+    float4* dout = F.aov[PTB_AOV_RADIANCE_DIRECT].acc; float4* iout = F.aov[PTB_AOV_RADIANCE_INDIRECT].acc;
+    if (F.config.enable_spatial_variance) {
+        k_svgf_variance<<<grid, 256, 0, st>>>(F, din, iin, dout, iout); (*launches)++;
+        float4* t = din; din = dout; dout = t; t = iin; iin = iout; iout = t;
+    }
+    for (int i = 0; i < F.config.num_atrous_iterations; i++) {
+        k_svgf_atrous<<<grid, 256, 0, st>>>(F, din, iin, dout, iout, 1 << i); (*launches)++;
+        float4* t = din; din = dout; dout = t; t = iin; iin = iout; iout = t;
+    }
+    k_svgf_finalize<<<grid, 256, 0, st>>>(F, din, iin); (*launches)++;
+    if (F.config.enable_taa) {
+        k_taa<<<grid, 256, 0, st>>>(F, sample_index); (*launches)++;
+        k_taa_finalize<<<grid, 256, 0, st>>>(F); (*launches)++;
+    }
+    k_clear_framebuffers<<<grid, 256, 0, st>>>(F); (*launches)++;
+    return 0;
+}

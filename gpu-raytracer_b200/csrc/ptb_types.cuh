@@ -65,6 +65,10 @@ struct RayTotals {                    // 64-bit running sums for Mrays/s, folded
     unsigned long long frames;
 };
 
+struct TraceStats {                   // [0] closest-hit, [1] shadow; filled only by the STATS kernel variants
+    unsigned long long rays, nodes, triangles, instance_transforms, misses;
+};
+
 struct AOVBuffers {
     float4* fb;   // written during the current pass
     float4* acc;  // running mean over passes
@@ -105,6 +109,7 @@ struct Frame {
     int*        matq[4];
     Counters*   counters;
     RayTotals*  totals;
+    TraceStats* trace_stats;
     AOVBuffers  aov[PTB_AOV_COUNT];
     float4*     display;              // what the reference writes to its GL surface
 

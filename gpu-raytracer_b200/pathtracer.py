@@ -62,9 +62,14 @@ class PtbRayStats(ctypes.Structure):
     _fields_ = [("trace", ctypes.c_uint64 * 128), ("shadow", ctypes.c_uint64 * 128), ("shaded", ctypes.c_uint64 * 4), ("frames", ctypes.c_uint64)]
 
 
+class PtbTraversalStats(ctypes.Structure):
+    _fields_ = [("rays", ctypes.c_uint64 * 2), ("nodes", ctypes.c_uint64 * 2), ("triangles", ctypes.c_uint64 * 2),
+                ("instance_transforms", ctypes.c_uint64 * 2), ("shadow_misses", ctypes.c_uint64)]
+
+
 # every symbol include/ptb.h declares (tests check the built library exports exactly these)
 ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render",
-               "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_download", "ptb_get_ray_stats", "ptb_get_stream", "ptb_export_rows",
+               "ptb_measure_traversal", "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_download", "ptb_get_ray_stats", "ptb_get_stream", "ptb_export_rows",
                "ptb_assemble_rows", "ptb_debug_read", "ptb_launch_count", "ptb_set_timing", "ptb_get_stage_ms", "ptb_stage_name",
                "ptb_error_string"]
 
@@ -85,6 +90,7 @@ def lib():
         l.ptb_set_camera.argtypes = [vp, ctypes.POINTER(PtbCamera), vp, vp]
         l.ptb_update_instances.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
         l.ptb_render.argtypes = [vp, ci]
+        l.ptb_measure_traversal.argtypes = [vp, ci, ctypes.POINTER(PtbTraversalStats)]
         l.ptb_sync.argtypes = [vp]
         l.ptb_get_aov.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(ci)]
         l.ptb_get_display.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci)]
@@ -298,6 +304,16 @@ class Pathtracer:
         _check(lib().ptb_debug_read(self._ctx, 1, out.ctypes.data, out.nbytes), "ptb_debug_read")
         o = out.reshape(8, 128)
         return dict(trace=o[0], diffuse=o[1], plastic=o[2], dielectric=o[3], conductor=o[4], shadow=o[5])
+
+    def measure_traversal(self, sample_index):
+        """One instrumented pass: node / triangle / instance-transform visit counts for closest-hit [0] and shadow [1] rays."""
+        if self.invalidated_camera or self.invalidated_gpu_config:
+            keep = self.sample_index
+            self.update(); self.sample_index = keep
+        st = PtbTraversalStats()
+        _check(lib().ptb_measure_traversal(self._ctx, int(sample_index), ctypes.byref(st)), "ptb_measure_traversal")
+        return dict(rays=list(st.rays), nodes=list(st.nodes), triangles=list(st.triangles),
+                    instance_transforms=list(st.instance_transforms), shadow_misses=int(st.shadow_misses))
 
     def launch_count(self):
         return int(lib().ptb_launch_count(self._ctx))

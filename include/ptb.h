@@ -114,6 +114,12 @@ typedef struct ptb_ray_stats {
     uint64_t frames;
 } ptb_ray_stats;
 
+/* Traversal work per ray kind ([0] closest hit, [1] shadow) for ONE pass, counted by an instrumented variant of the
+ * trace kernel: the inputs of SURVEY.md section 8d's algorithmic-bytes formula. */
+typedef struct ptb_traversal_stats {
+    uint64_t rays[2], nodes[2], triangles[2], instance_transforms[2], shadow_misses;
+} ptb_traversal_stats;
+
 /* Pathtracer(gl_tex, width, height, scene) + cuda_init/resize_init (Pathtracer.h:260, Pathtracer.cpp:9-41,255-301).
  * rank/world: this ctx traces the rows ((y / band_rows) % world == rank); world = 1 renders the whole frame. */
 int  ptb_create(ptb_ctx** out, int device, int width, int height, int rank, int world, int band_rows);
@@ -131,6 +137,8 @@ int  ptb_update_instances(ptb_ctx* ctx, const void* tlas_nodes, int tlas_node_co
                           const float* transforms, const float* transforms_inv, const float* transforms_prev);
 /* Pathtracer::render() for one pass with the given sample_index (Pathtracer.cpp:738-855). Asynchronous on the ctx stream. */
 int  ptb_render(ptb_ctx* ctx, int sample_index);
+/* Same as ptb_render, with the instrumented trace kernels; blocks and returns the pass's traversal statistics. */
+int  ptb_measure_traversal(ptb_ctx* ctx, int sample_index, ptb_traversal_stats* out);
 /* cuStreamSynchronize equivalent */
 int  ptb_sync(ptb_ctx* ctx);
 /* get_aov(type).framebuffer / .accumulator (Integrator.h:247): device pointer to pitch x height float4 */

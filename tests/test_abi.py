@@ -1,0 +1,63 @@
+"""The C-ABI shared library builds, loads without a GPU, exports exactly what include/ptb.h declares, and fails
+loudly (no CPU fallback) when asked to create a context without a CUDA device."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT, has_gpu
+from gpu_raytracer_b200 import build, pathtracer as pt
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "ptb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ptb_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert header_symbols() == sorted(pt.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    path = build.build_cuda()
+    lib = ctypes.CDLL(path)
+    for name in header_symbols():
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (ptb_[a-z_0-9]+)", out))
+    assert exported == set(header_symbols())
+
+
+def test_struct_sizes_match_reference_abi():
+    assert ctypes.sizeof(pt.PtbConfig) == 44      # GPUConfig, Common.h:39-67
+    assert ctypes.sizeof(pt.PtbCamera) == 60      # CUDACamera, Integrator.cpp:456-472
+    assert ctypes.sizeof(pt.PtbRayStats) == 8 * (128 + 128 + 4 + 1)
+
+
+def test_library_contains_sm100a_code_and_tma():
+    path = build.build_cuda()
+    sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "UBLKCP" in sass          # cp.async.bulk (TMA 1-D bulk copy) staging the TLAS into shared memory
+    for kernel in ("k_trace8", "k_sort", "k_shade", "k_generate", "k_accumulate"):
+        assert kernel in sass
+
+
+@pytest.mark.skipif(has_gpu(), reason="this asserts the no-GPU failure mode")
+def test_no_gpu_means_error_not_fallback():
+    lib = pt.lib()
+    ctx = ctypes.c_void_p()
+    code = lib.ptb_create(ctypes.byref(ctx), 0, 64, 64, 0, 1, 8)
+    assert code != 0 and not ctx.value
+    assert lib.ptb_error_string(code)
+
+
+def test_bad_arguments_are_rejected():
+    lib = pt.lib()
+    ctx = ctypes.c_void_p()
+    assert lib.ptb_create(ctypes.byref(ctx), 0, 0, 64, 0, 1, 8) == -1
+    assert lib.ptb_create(ctypes.byref(ctx), 0, 64, 64, 2, 2, 8) == -1
+    assert lib.ptb_render(None, 0) == -1

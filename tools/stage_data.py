@@ -99,13 +99,13 @@ def main():
     stage_rng()
     which = sys.argv[1:] or ["cornellbox", "cornellbox_bvh8", "sponza", "instancing"]
     if "cornellbox" in which:
-        stage_scene("cornellbox", "Data/cornellbox/scene.xml", 512, 512, 1, 2, sky_max_width=1250)
+        stage_scene("cornellbox", "Data/cornellbox/scene.xml", 512, 512, 1, 2, sky_max_width=625)
     if "cornellbox_bvh8" in which:
-        stage_scene("cornellbox_bvh8", "Data/cornellbox/scene.xml", 512, 512, 4, 8, sky_max_width=1250)
+        stage_scene("cornellbox_bvh8", "Data/cornellbox/scene.xml", 512, 512, 4, 8, sky_max_width=625)
     if "sponza" in which:
-        stage_scene("sponza", "Data/Sponza/scene.xml", 1920, 1080, 4, 8)
+        stage_scene("sponza", "Data/Sponza/scene.xml", 1920, 1080, 4, 8, sky_max_width=1250)
     if "instancing" in which:
-        stage_scene("instancing", "Data/instancing/scene.xml", 1920, 1080, 4, 8, sky_max_width=1250)
+        stage_scene("instancing", "Data/instancing/scene.xml", 1920, 1080, 4, 8, sky_max_width=625)
 
 
 if __name__ == "__main__":
