@@ -242,7 +242,7 @@ def main():
 
     mx_rows = tiles.max_owned_rows(HEIGHT, world, args.band_rows)
     packed = torch.zeros((mx_rows, p.screen_pitch, 4), dtype=torch.float32, device="cuda")
-    gathered = torch.empty((world, mx_rows, p.screen_pitch, 4), dtype=torch.float32, device="cuda") if world > 1 else None
+    gathered = torch.empty((world * mx_rows, p.screen_pitch, 4), dtype=torch.float32, device="cuda") if world > 1 else None   # rank-major
     frame = torch.empty((HEIGHT, p.screen_pitch, 4), dtype=torch.float32, device="cuda") if world > 1 else None
     host_frame = torch.empty((HEIGHT, p.screen_pitch, 4), dtype=torch.float32).pin_memory()
 

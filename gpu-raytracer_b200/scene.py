@@ -593,7 +593,7 @@ def pack_triangles(p, n, t):
     return out
 
 
-def build_blob(desc: SceneDesc, bvh_kind=8, width=None, height=None, threads=None, timing=None):
+def build_blob(desc: SceneDesc, bvh_kind=8, width=None, height=None, threads=None, timing=None, rng="auto"):
     """Flatten a SceneDesc into the device ABI. `timing` (dict) receives the CPU BVH-build seconds."""
     import time
     width = int(width or desc.width); height = int(height or desc.height)
@@ -701,7 +701,10 @@ def build_blob(desc: SceneDesc, bvh_kind=8, width=None, height=None, threads=Non
                 lm_cdf.append(total_w); lm_span.append((first, last)); lm_xf.append(slot)
     lm_cdf = (np.array(lm_cdf, dtype=f32) / f32(total_w)).astype(f32) if lm_cdf else np.zeros(0, dtype=f32)
 
-    pmj, blue, rng_src = load_rng_tables()
+    if rng == "fallback":
+        pmj, blue = fallback_rng_tables(); rng_src = "fallback"
+    else:
+        pmj, blue, rng_src = load_rng_tables()
     sky = desc.sky if desc.sky is not None else procedural_sky()
     blob = dict(
         bvh_kind=int(bvh_kind), width=width, height=height, num_bounces=int(desc.num_bounces),
@@ -1033,6 +1036,18 @@ def procedural_scene(kind="atrium", seed=7, width=256, height=256, detail=1.0, a
                  d.add_material(Material(MAT_DIELECTRIC, "glass", ior=1.5, roughness=0.3)),
                  d.add_material(Material(MAT_CONDUCTOR, "gold", eta=(1.45, 0.43, 0.21), k=(1.95, 2.46, 3.27), roughness=0.3)),
                  d.add_material(Material(MAT_DIELECTRIC, "smooth_glass", ior=1.33, roughness=0.0))]
+    if kind == "cornell":
+        # the classic box: five walls, two blocks, one ceiling lamp (own dimensions; all instances identity like the reference's primitives)
+        rot = lambda ax, a: m_rotation(q_axis_angle(ax, a))
+        walls = [(m_translate((0, 0, 0)) @ rot((1, 0, 0), -math.pi / 2), white), (m_translate((0, 2, 0)) @ rot((1, 0, 0), math.pi / 2), white),
+                 (m_translate((0, 1, -1)), white), (m_translate((-1, 1, 0)) @ rot((0, 1, 0), math.pi / 2), red), (m_translate((1, 1, 0)) @ rot((0, 1, 0), -math.pi / 2), green)]
+        for m, mat in walls:
+            d.instances.append(Instance(d.add_mesh_data(geo_rectangle(m)), mat))
+        d.instances.append(Instance(d.add_mesh_data(geo_cube(m_translate((0.33, 0.3, 0.35)) @ rot((0, 1, 0), -0.3) @ m_scale(0.3))), white))
+        d.instances.append(Instance(d.add_mesh_data(geo_cube(m_translate((-0.34, 0.6, -0.3)) @ rot((0, 1, 0), 0.33) @ m_scale(0.3, 0.6, 0.3))), white))
+        d.instances.append(Instance(d.add_mesh_data(geo_rectangle(m_translate((0, 1.98, 0)) @ rot((1, 0, 0), math.pi / 2) @ m_scale(0.24, 0.19, 1.0))), light))
+        d.cam_position = np.array([0.0, 1.0, 3.4]); d.cam_rotation = np.array([0.0, 0.0, 0.0, 1.0]); d.cam_fov = math.radians(40)
+        return d
     if kind == "soup":
         n = max(8, int(400 * detail))
         soup = d.add_mesh_data(_soup(rng, n, 1.0, 0.15))

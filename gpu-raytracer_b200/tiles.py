@@ -59,7 +59,7 @@ def gather_frame_torch(pathtracer, aov_type=0):
     with torch.cuda.stream(st):
         packed = torch.zeros((mx, p.screen_pitch, 4), dtype=torch.float32, device="cuda")
         p.export_rows(packed.data_ptr(), aov_type)
-        gathered = torch.empty((world, mx, p.screen_pitch, 4), dtype=torch.float32, device="cuda")
+        gathered = torch.empty((world * mx, p.screen_pitch, 4), dtype=torch.float32, device="cuda")   # rank-major concatenation
         dist.all_gather_into_tensor(gathered, packed)
         frame = torch.empty((p.screen_height, p.screen_pitch, 4), dtype=torch.float32, device="cuda")
         p.assemble_rows(gathered.data_ptr(), mx, frame.data_ptr())

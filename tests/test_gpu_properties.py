@@ -1,0 +1,101 @@
+"""Size-independent properties at BASELINE.json's full sizes + edge cases (GPU, through the C ABI)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from gpu_raytracer_b200 import pathtracer as pt, scene, tiles
+
+pytestmark = pytest.mark.gpu
+
+
+def full_size_blob():
+    staged = os.path.join(ROOT, "data", "_staged", "sponza.npz")
+    if os.path.exists(staged):
+        return scene.load_blob(staged)
+    return scene.build_blob(scene.procedural_scene("atrium", seed=7, width=1920, height=1080, detail=2.0), 8, 1920, 1080)
+
+
+@pytest.fixture(scope="module")
+def big():
+    return full_size_blob()
+
+
+def test_full_size_determinism_and_accumulation(big):
+    """1080p, 4 bounces: two independent contexts give bit-identical frames; pass 0 does not survive in the accumulator;
+    acc after passes 0..2 == mean of the framebuffers of passes 1 and 2 (online mean, AOV.h:35-46)."""
+    cfg = pt.default_config(num_bounces=4)
+    a = pt.Pathtracer(big, config=cfg); b = pt.Pathtracer(big, config=cfg)
+    a.render_frames(2)
+    b.render_pass(1); b.sync(); f1 = b.get_aov(0).astype(np.float32)       # sample_index 1 on a fresh accumulator: acc = fb
+    c = pt.Pathtracer(big, config=cfg); c.render_pass(0); c.render_pass(1); c.sync()
+    assert np.array_equal(c.get_aov(0).view(np.uint32), f1.view(np.uint32))  # pass 0 overwritten
+    b2 = pt.Pathtracer(big, config=cfg); b2.render_frames(2)
+    assert np.array_equal(a.get_aov(0).view(np.uint32), b2.get_aov(0).view(np.uint32))
+    st = a.ray_stats()
+    assert st["trace"][0] == 3 * 1920 * 1080 and st["trace"][4] == 0
+    assert (st["trace"][1:4] <= st["trace"][0:3]).all() and (st["shadow"][:4] <= st["trace"][:4]).all()
+    for p in (a, b, c, b2):
+        p.close()
+
+
+def test_tile_sharding_is_partition_invariant(big):
+    """world=3 ranks (all on this GPU) each trace their row bands; packed+assembled frame == the 1-GPU frame bit for bit."""
+    import torch
+    cfg = pt.default_config(num_bounces=3)
+    whole = pt.Pathtracer(big, config=cfg); whole.render_frames(1)
+    ref_img = whole.get_aov(0)
+    world, band = 3, 8
+    mx = tiles.max_owned_rows(1080, world, band)
+    gathered = torch.zeros((world, mx, whole.screen_pitch, 4), dtype=torch.float32, device="cuda")
+    frame = torch.zeros((1080, whole.screen_pitch, 4), dtype=torch.float32, device="cuda")
+    rays = 0
+    for r in range(world):
+        p = pt.Pathtracer(big, rank=r, world=world, band_rows=band, config=cfg)
+        p.render_frames(1)
+        rows = p.export_rows(gathered[r].data_ptr()); p.sync()
+        assert rows == len(tiles.owned_rows(1080, r, world, band))
+        rays += int(p.ray_stats()["trace"].sum())
+        if r == world - 1:
+            p.assemble_rows(gathered.data_ptr(), mx, frame.data_ptr()); p.sync()
+        p.close()
+    out = frame.cpu().numpy()
+    assert np.array_equal(out[:, :1920].view(np.uint32), ref_img[:, :1920].view(np.uint32))
+    assert rays == int(whole.ray_stats()["trace"].sum())
+    # numpy mirror of the assemble kernel agrees with the kernel
+    assert np.array_equal(tiles.assemble_rows(gathered.cpu().numpy(), 1080, world, band)[:, :1920], out[:, :1920])
+    whole.close()
+
+
+def test_edge_cases():
+    # width not a multiple of 32 (pitch padding), one bounce, no lights, a single triangle
+    d = scene.procedural_scene("soup", seed=2, width=70, height=33, detail=0.1)
+    blob = scene.build_blob(d, 8, rng="fallback")
+    p = pt.Pathtracer(blob, config=pt.default_config(num_bounces=1)); p.render_frames(1)
+    img = p.get_aov(0)
+    assert img.shape == (33, 96, 4) and np.isfinite(img).all() and not img[:, 70:].any()
+    assert p.ray_stats()["shadow"].sum() == 0       # the last bounce terminates in the sort pass
+    p.close()
+    d = scene.SceneDesc(); d.width, d.height, d.num_bounces = 64, 48, 3
+    m = d.add_material(scene.Material(scene.MAT_DIFFUSE, diffuse=(0.5, 0.5, 0.5)))
+    tri = scene.finish_triangles([[[-1, -1, -3], [1, -1, -3], [0, 1, -3]]], [[[0, 0, 1]] * 3], [[[0, 0], [1, 0], [0, 1]]])
+    d.instances.append(scene.Instance(d.add_mesh_data(tri), m))
+    blob = scene.build_blob(d, 8, rng="fallback")
+    assert blob["light_mesh_cdf"].size == 0
+    p = pt.Pathtracer(blob); p.render_frames(2)
+    st = p.ray_stats()
+    assert st["shadow"].sum() == 0 and st["trace"][0] == 3 * 64 * 48 and 0 < st["shaded"][0] < st["trace"][0]
+    assert np.isfinite(p.get_aov(0)).all()
+    p.close()
+
+
+def test_errors_are_reported_not_swallowed():
+    import ctypes
+    lib = pt.lib()
+    ctx = ctypes.c_void_p()
+    assert lib.ptb_create(ctypes.byref(ctx), 0, 64, 64, 0, 1, 8) == 0
+    assert lib.ptb_render(ctx, 0) == -2                      # no scene uploaded
+    bad = pt.default_config(num_bounces=0)
+    assert lib.ptb_set_config(ctx, ctypes.byref(bad)) == -1
+    lib.ptb_destroy(ctx)

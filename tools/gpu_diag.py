@@ -58,6 +58,16 @@ def main():
         diag("atrium", scene.build_blob(scene.procedural_scene("atrium", seed=3, width=640, height=360), 8))
     if "sponza" in which:
         diag("sponza", scene.load_blob(os.path.join(staged, "sponza.npz")), max_nb=3)
+    for kind, mat in (("plastic", scene.Material(scene.MAT_PLASTIC, "p", diffuse=(0.2, 0.8, 0.8), roughness=0.2)),
+                      ("dielectric", scene.Material(scene.MAT_DIELECTRIC, "d", ior=1.5, roughness=0.3)),
+                      ("smoothglass", scene.Material(scene.MAT_DIELECTRIC, "s", ior=1.33, roughness=0.0)),
+                      ("conductor", scene.Material(scene.MAT_CONDUCTOR, "c", eta=(1.45, 0.43, 0.21), k=(1.95, 2.46, 3.27), roughness=0.3))):
+        if kind in which:
+            d = scene.procedural_scene("soup", seed=3, width=256, height=256)
+            m = d.add_material(mat)
+            for inst in d.instances[3:7]:
+                inst.material = m
+            diag(kind, scene.build_blob(d, 8, rng="fallback"))
     if "sponza_nomip" in which:
         diag("sponza_nomip", scene.load_blob(os.path.join(staged, "sponza.npz")), max_nb=2, enable_mipmapping=0)
 
