@@ -44,11 +44,13 @@ def cuda_sources():
     return sorted(glob.glob(os.path.join(d, "*.cu"))), sorted(glob.glob(os.path.join(d, "*.cuh")) + glob.glob(os.path.join(REPO_ROOT, "include", "*.h")))
 
 
-def build_cuda(force=False, verbose=False):
+def build_cuda(force=False, verbose=False, defines=(), suffix=""):
+    """defines/suffix build tuning variants (libptb<suffix>.so) for A/B measurements; the product is the plain libptb.so."""
     srcs, hdrs = cuda_sources()
-    out = os.path.join(PKG_DIR, "csrc", "libptb.so")
+    out = os.path.join(PKG_DIR, "csrc", f"libptb{suffix}.so")
     if force or _stale(out, srcs + hdrs):
         cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC", "-shared",
+               *[f"-D{d}" for d in defines],
                "-I", os.path.join(REPO_ROOT, "include"), "-I", os.path.join(PKG_DIR, "csrc"), "-o", out, *srcs]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

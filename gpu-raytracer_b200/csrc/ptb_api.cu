@@ -594,6 +594,28 @@ extern "C" int ptb_debug_read(ptb_ctx* ctx, int which, void* host_dst, int64_t b
         CK(cudaStreamSynchronize(ctx->stream));
         return 0;
     }
+    if (which >= 10 && which <= 17) {   // SVGF state (pitch x height elements)
+        const Frame& F = ctx->F;
+        const void* src[8] = { F.svgf.history_normal_depth, F.svgf.history_direct, F.svgf.history_indirect, F.svgf.history_moment,
+                               F.svgf.moment, F.svgf.taa_curr, F.svgf.taa_prev, F.svgf.history_length };
+        size_t elem = which == 17 ? sizeof(int) : sizeof(float4);
+        size_t need = (size_t)F.pitch * F.height * elem;
+        if (!src[which - 10] || (size_t)bytes < need) return PTB_E_BADARG;
+        CK(cudaMemcpyAsync(host_dst, src[which - 10], need, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    if (which == 2) {   // Kulla-Conty LUT contents
+        const size_t n = 2 * 16 * 16 * 16 + 2 * 16 * 16 + 32 * 32 + 32;
+        if ((size_t)bytes < n * sizeof(float) || !ctx->luts_ready) return PTB_E_BADARG;
+        float* d = nullptr;
+        CK(cudaMalloc(&d, n * sizeof(float)));
+        k_dump_luts<<<(16 * 16 * 16 + 255) / 256, 256, 0, ctx->stream>>>(ctx->F, d); ctx->launches++;
+        CK(cudaMemcpyAsync(host_dst, d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d);
+        return 0;
+    }
     return PTB_E_BADARG;
 }
 extern "C" int64_t ptb_launch_count(ptb_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -180,6 +180,18 @@ PTB_DI unsigned ray_octant_inv4(float3 d) {
     return (d.x < 0.0f ? 0u : 0x04040404u) | (d.y < 0.0f ? 0u : 0x02020202u) | (d.z < 0.0f ? 0u : 0x01010101u);
 }
 
+// byte j of x as a float.  Two exact routes: I2F.U8 (XU pipe, quarter rate -- ncu showed the XU pipe 73 % busy with the 48
+// conversions per node) or the 2^23 magic number: PRMT builds the bits of (8388608 + byte), one FADD (FMA pipe) removes the bias.
+// Both give the same float bit pattern; PTB_CVT_MAGIC_MASK picks, per use site, which pipe pays (bit 0..5 = xmin,ymin,zmin,xmax,ymax,zmax).
+#ifndef PTB_CVT_MAGIC_MASK
+#define PTB_CVT_MAGIC_MASK 0x00
+#endif
+template <int SITE>
+PTB_DI float byte_to_float(unsigned x, int j) {
+    if ((PTB_CVT_MAGIC_MASK >> SITE) & 1) return __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7540u | unsigned(j))) - 8388608.0f;
+    return float(byte_of(x, j));
+}
+
 PTB_DI unsigned cwbvh_node_intersect(const Ray& ray, unsigned oct_inv4, float max_distance, float4 n0, float4 n1, float4 n2, float4 n3, float4 n4) {
     float3 p = f3(n0.x, n0.y, n0.z);
     unsigned e_imask = __float_as_uint(n0.w);
@@ -203,8 +215,8 @@ PTB_DI unsigned cwbvh_node_intersect(const Ray& ray, unsigned oct_inv4, float ma
         unsigned z_min = ray.d.z < 0.0f ? qhz : qlz, z_max = ray.d.z < 0.0f ? qlz : qhz;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            float3 tmin3 = f3(float(byte_of(x_min, j)), float(byte_of(y_min, j)), float(byte_of(z_min, j)));
-            float3 tmax3 = f3(float(byte_of(x_max, j)), float(byte_of(y_max, j)), float(byte_of(z_max, j)));
+            float3 tmin3 = f3(byte_to_float<0>(x_min, j), byte_to_float<1>(y_min, j), byte_to_float<2>(z_min, j));
+            float3 tmax3 = f3(byte_to_float<3>(x_max, j), byte_to_float<4>(y_max, j), byte_to_float<5>(z_max, j));
             tmin3 = tmin3 * adj_inv + adj_org;
             tmax3 = tmax3 * adj_inv + adj_org;
             float tmin = imax3(tmin3.x, tmin3.y, fmaxf(tmin3.z, 0.0f));

@@ -71,7 +71,8 @@ PTB_DI float3 safe_sqrt(float3 v) { return f3(safe_sqrt(v.x), safe_sqrt(v.y), sa
 PTB_DI float abs_dot(float3 a, float3 b) { return fabsf(dot(a, b)); }
 PTB_DI float sign1(float x) { return copysignf(1.0f, x); }
 PTB_DI float luminance(float r, float g, float b) { return 0.299f * r + 0.587f * g + 0.114f * b; }
-PTB_DI float lerpf(float a, float b, float t) { return (1.0f - t) * a + t * b; }
+// NVIDIA helper_math lerp (a + t*(b-a)): in the reference the non-template helper_math overload wins over Util.h's template
+PTB_DI float lerpf(float a, float b, float t) { return a + t * (b - a); }
 PTB_DI float2 sincos2(float x) { float s, c; __sincosf(x, &s, &c); return f2(s, c); }
 template <typename T> PTB_DI T barycentric(float u, float v, T base, T e1, T e2) { return base + u * e1 + v * e2; }
 

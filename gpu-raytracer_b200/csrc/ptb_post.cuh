@@ -101,3 +101,22 @@ __global__ void k_average_conductor(const float* dir, float* out) {
     out[tid] = 2.0f * avg;
 }
 
+
+// debug/parity tap: the six LUTs sampled at their texel centres -> 2*16^3 + 2*16^2 + 32^2 + 32 floats
+__global__ void k_dump_luts(const __grid_constant__ Frame P, float* out) {
+    const int D = PTB_LUT_DIELECTRIC_DIM, C = PTB_LUT_CONDUCTOR_DIM;
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < D * D * D) {
+        int i = tid % D, r = (tid / D) % D, c = tid / (D * D);
+        float u = (i + 0.5f) / D, v = (r + 0.5f) / D, w = (c + 0.5f) / D;
+        out[tid] = tex3D<float>(P.lut_dielectric_dir_enter, u, v, w);
+        out[D * D * D + tid] = tex3D<float>(P.lut_dielectric_dir_leave, u, v, w);
+    }
+    if (tid < D * D) {
+        float u = (tid % D + 0.5f) / D, v = (tid / D + 0.5f) / D;
+        out[2 * D * D * D + tid] = tex2D<float>(P.lut_dielectric_enter, u, v);
+        out[2 * D * D * D + D * D + tid] = tex2D<float>(P.lut_dielectric_leave, u, v);
+    }
+    if (tid < C * C) out[2 * D * D * D + 2 * D * D + tid] = tex2D<float>(P.lut_conductor_dir, (tid % C + 0.5f) / C, (tid / C + 0.5f) / C);
+    if (tid < C) out[2 * D * D * D + 2 * D * D + C * C + tid] = tex1D<float>(P.lut_conductor, (tid + 0.5f) / C);
+}

@@ -12,8 +12,9 @@ PTB_DI float4 gbuf_nd(const Frame& P, int x, int y) {
     x = min(max(x, 0), P.pitch - 1); y = min(max(y, 0), P.height - 1);
     return P.svgf.gbuf_normal_depth[x + y * P.pitch];
 }
-PTB_DI float4 lerp4(float4 a, float4 b, float t) { return (1.0f - t) * a + t * b; }
-PTB_DI float3 lerp3(float3 a, float3 b, float t) { return (1.0f - t) * a + t * b; }
+// helper_math lerp semantics (see lerpf)
+PTB_DI float4 lerp4(float4 a, float4 b, float t) { return a + t * (b - a); }
+PTB_DI float3 lerp3(float3 a, float3 b, float t) { return a + t * (b - a); }
 
 PTB_DI bool tap_consistent(const Frame& P, int x, int y, float3 normal, float depth) {
     if (x < 0 || x >= P.width) return false;

@@ -80,7 +80,7 @@ def lib():
     """Loads libptb.so (building it if stale). Raises if it cannot be built or loaded -- there is no fallback."""
     global _lib
     if _lib is None:
-        path = _build.build_cuda()
+        path = os.environ.get("PTB_LIB_PATH") or _build.build_cuda()      # PTB_LIB_PATH: A/B tuning variants only
         l = ctypes.CDLL(path)
         vp, ci = ctypes.c_void_p, ctypes.c_int
         l.ptb_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, ci]
@@ -314,6 +314,24 @@ class Pathtracer:
         _check(lib().ptb_measure_traversal(self._ctx, int(sample_index), ctypes.byref(st)), "ptb_measure_traversal")
         return dict(rays=list(st.rays), nodes=list(st.nodes), triangles=list(st.triangles),
                     instance_transforms=list(st.instance_transforms), shadow_misses=int(st.shadow_misses))
+
+    SVGF_TAPS = {"history_normal_and_depth": 10, "history_direct": 11, "history_indirect": 12, "history_moment": 13,
+                 "frame_buffer_moment": 14, "taa_frame_curr": 15, "taa_frame_prev": 16, "history_length": 17}
+
+    def svgf_buffer(self, name):
+        which = self.SVGF_TAPS[name]
+        if which == 17:
+            out = np.empty((self.screen_height, self.screen_pitch), dtype=np.int32)
+        else:
+            out = np.empty((self.screen_height, self.screen_pitch, 4), dtype=np.float32)
+        _check(lib().ptb_debug_read(self._ctx, which, out.ctypes.data, out.nbytes), "ptb_debug_read")
+        return out
+
+    def lut_contents(self):
+        n = 2 * 16 ** 3 + 2 * 16 ** 2 + 32 ** 2 + 32
+        out = np.empty(n, dtype=np.float32)
+        _check(lib().ptb_debug_read(self._ctx, 2, out.ctypes.data, out.nbytes), "ptb_debug_read")
+        return out
 
     def launch_count(self):
         return int(lib().ptb_launch_count(self._ctx))

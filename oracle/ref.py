@@ -89,6 +89,21 @@ class Reference:
         return dict(trace=np.array(st.trace[:], dtype=np.uint64), shadow=np.array(st.shadow[:], dtype=np.uint64),
                     shaded=np.array(st.shaded[:], dtype=np.uint64), frames=int(st.frames))
 
+    def svgf_buffer(self, name):
+        if name == "history_length":
+            out = np.empty((self.height, self.pitch), dtype=np.int32)
+        else:
+            out = np.empty((self.height, self.pitch, 4), dtype=np.float32)
+        l = lib(); l.ref_read_global_buffer.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
+        self._ck(l.ref_read_global_buffer(self._ctx, name.encode(), ctypes.c_void_p(out.ctypes.data), out.nbytes), "ref_read_global_buffer")
+        return out
+
+    def lut_contents(self):
+        n = 2 * 16 ** 3 + 2 * 16 ** 2 + 32 ** 2 + 32
+        out = np.empty(n, dtype=np.float32)
+        self._ck(lib().ref_read_luts(self._ctx, ctypes.c_void_p(out.ctypes.data)), "ref_read_luts")
+        return out
+
     def set_timing(self, on=True):
         lib().ref_set_timing(self._ctx, int(on))
 

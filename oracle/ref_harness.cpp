@@ -59,6 +59,7 @@ struct ref_ctx {
     CUdeviceptr trace_hits[2] = {}, trace_pix[2] = {};
     BufferSizes sizes;
     uint64_t total_trace[MAX_BOUNCES] = {}, total_shadow[MAX_BOUNCES] = {}, total_shaded[4] = {}, frames = 0;
+    CUarray lut_arrays[6] = {};   // dielectric dir enter/leave, dielectric avg enter/leave, conductor dir, conductor avg
     bool svgf_ready = false;
     CUdeviceptr history_ptrs[5] = {};
     bool timing = false;
@@ -240,6 +241,7 @@ static int bake_luts(ref_ctx* c) {   // Pathtracer.cpp:182-245
         e = make_array_texture(a_avg, &t_avg); if (e) return e;
         e = set_global(c, dir_names[pass], t_dir); if (e) return e;
         e = set_global(c, avg_names[pass], t_avg); if (e) return e;
+        c->lut_arrays[pass] = a_dir; c->lut_arrays[2 + pass] = a_avg;
     }
     CUdeviceptr d_dir, d_avg;
     e = dalloc(c, &d_dir, 32 * 32 * 4); if (e) return e;
@@ -266,6 +268,7 @@ static int bake_luts(ref_ctx* c) {   // Pathtracer.cpp:182-245
     e = make_array_texture(a_avg, &t_avg); if (e) return e;
     e = set_global(c, "lut_conductor_directional_albedo", t_dir); if (e) return e;
     e = set_global(c, "lut_conductor_albedo", t_avg); if (e) return e;
+    c->lut_arrays[4] = a_dir; c->lut_arrays[5] = a_avg;
     return 0;
 }
 
@@ -563,6 +566,38 @@ int ref_get_ray_stats(ref_ctx* c, ptb_ray_stats* out, int reset) {
     memcpy(out->trace, c->total_trace, sizeof(c->total_trace)); memcpy(out->shadow, c->total_shadow, sizeof(c->total_shadow));
     memcpy(out->shaded, c->total_shaded, sizeof(c->total_shaded)); out->frames = c->frames;
     if (reset) { memset(c->total_trace, 0, sizeof(c->total_trace)); memset(c->total_shadow, 0, sizeof(c->total_shadow)); memset(c->total_shaded, 0, sizeof(c->total_shaded)); c->frames = 0; }
+    return 0;
+}
+
+// LUT contents in the layout of ptb's k_dump_luts: 2*16^3 + 2*16^2 + 32^2 + 32 floats
+int ref_read_luts(ref_ctx* c, float* out) {
+    RCK(cuCtxSetCurrent(c->cu));
+    RCK(cuCtxSynchronize());
+    int dims[6][3] = { { 16, 16, 16 }, { 16, 16, 16 }, { 16, 16, 1 }, { 16, 16, 1 }, { 32, 32, 1 }, { 32, 1, 1 } };
+    int order[6] = { 0, 1, 2, 3, 4, 5 };
+    size_t off = 0;
+    for (int k = 0; k < 6; k++) {
+        int i = order[k];
+        CUDA_MEMCPY3D cp; memset(&cp, 0, sizeof(cp));
+        cp.srcMemoryType = CU_MEMORYTYPE_ARRAY; cp.srcArray = c->lut_arrays[i];
+        cp.dstMemoryType = CU_MEMORYTYPE_HOST; cp.dstHost = out + off; cp.dstPitch = (size_t)dims[i][0] * 4; cp.dstHeight = dims[i][1];
+        cp.WidthInBytes = (size_t)dims[i][0] * 4; cp.Height = dims[i][1]; cp.Depth = dims[i][2];
+        RCK(cuMemcpy3D(&cp));
+        off += (size_t)dims[i][0] * dims[i][1] * dims[i][2];
+    }
+    return 0;
+}
+
+// Reads `bytes` from the device buffer a pointer-typed module global points to (parity taps for the SVGF state)
+int ref_read_global_buffer(ref_ctx* c, const char* global_name, void* dst, size_t bytes) {
+    RCK(cuCtxSetCurrent(c->cu));
+    RCK(cuCtxSynchronize());
+    CUdeviceptr g; size_t sz;
+    int e = get_global(c, global_name, &g, &sz); if (e) return e;
+    CUdeviceptr p = 0;
+    RCK(cuMemcpyDtoH(&p, g, sizeof(p)));
+    if (!p) return 1;
+    RCK(cuMemcpyDtoH(dst, p, bytes));
     return 0;
 }
 
