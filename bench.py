@@ -116,7 +116,7 @@ def cpu_baseline(blob, budget_s=12.0):
     o = Oracle(blob, num_bounces=BOUNCES, threads=cores)
     rows_done, t_total, rays = 0, 0.0, 0
     y = 0
-    step = 8
+    step = 72                  # tall bands keep all host cores busy (OpenMP over rows)
     while t_total < budget_s and y + step <= o.height:
         before = int(o.counters.sum())
         t0 = time.perf_counter()
@@ -124,9 +124,9 @@ def cpu_baseline(blob, budget_s=12.0):
         t_total += time.perf_counter() - t0
         rays += int(o.counters.sum()) - before
         rows_done += step
-        y += step * 9          # spread the sampled bands over the frame
-        if y + step > o.height and rows_done < 64:
-            y = (rows_done // step) % 9 * step + step
+        y += step * 3          # spread the sampled bands over the frame
+        if y + step > o.height and rows_done < 360:
+            y = step
     return dict(value=rays / t_total / 1e6, unit="Mrays/s", cores=cores, kind="port",
                 sample=f"{rows_done} rows x {o.width} px x 1 pass of the same frame ({rays} rays in {t_total:.1f} s), oracle/pt_oracle.c with OpenMP")
 
@@ -247,9 +247,7 @@ def main():
     host_frame = torch.empty((HEIGHT, p.screen_pitch, 4), dtype=torch.float32).pin_memory()
 
     def one_frame(gather=True):
-        p.invalidated_gpu_config = True           # new frame: sample_index restarts at 0 (Integrator.cpp:518-521)
-        for _ in range(PASSES_PER_STEP):
-            p.update(); p.render()
+        p.render_frame(PASSES_PER_STEP - 1)       # sample_index 0..8 (Integrator.cpp:518-526), replayed as one CUDA graph
         if world > 1 and gather:
             with torch.cuda.stream(stream):
                 p.export_rows(packed.data_ptr(), pt.AOV_RADIANCE)
@@ -268,8 +266,6 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = p.launch_count()
-    p.set_timing(True)
-    stage_tot = {}
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
@@ -281,8 +277,6 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     p.sync()
-    last_pass_stages = p.stage_ms()                  # stage device times of the LAST pass of the timed region (CUDA events per stage)
-    p.set_timing(False)
     launches = p.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     st = p.ray_stats(reset=True)
@@ -296,10 +290,12 @@ def main():
     p.set_timing(True)
     trace_ms = shadow_ms = 0.0
     n_trace_launch = n_shadow_launch = 0
-    p.invalidated_gpu_config = True
-    for _ in range(PASSES_PER_STEP):
-        p.update(); p.render(); p.sync()
+    stage_frame = {}
+    for si in range(PASSES_PER_STEP):
+        p.render_pass(si); p.sync()
         sm = p.stage_ms()
+        for k, v in sm.items():
+            stage_frame[k] = stage_frame.get(k, 0.0) + v
         trace_ms += sm["trace"]; shadow_ms += sm["shadow_trace"]
         n_trace_launch += BOUNCES; n_shadow_launch += BOUNCES
     p.set_timing(False)
@@ -368,7 +364,7 @@ def main():
                            "l2": "working set (ray queues + AOVs > 400 MB per pass) exceeds the 126 MB L2", "rng_tables": blob.get("rng_source", "?"),
                            "ms_per_frame": ms_max / args.steps},
                 "rays_per_step": int(rays_total / args.steps), "clocks": clocks, "gpu_launches": int(launches),
-                "stage_ms_last_pass": last_pass_stages,
+                "stage_ms_per_frame": stage_frame,
                 "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(host_frame.numel() * 4), "ms_per_step": float(t.item()) / args.steps},
                 "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:

@@ -70,7 +70,11 @@ struct ptb_ctx {
     bool luts_ready = false;
     uint4* tap_hits = nullptr;
     long long launches = 0;
+    long long launches_per_pass = 0;
     bool stats_mode = false;
+    struct FrameGraph { int first, passes; cudaGraphExec_t exec; };
+    std::vector<FrameGraph> graphs;
+    bool capturing = false;
     bool timing = false;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;
     std::vector<cudaEvent_t> event_pool;
@@ -81,6 +85,8 @@ struct ptb_ctx {
     std::string last_error;
     float4* svgf_ping[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };
 };
+
+static void drop_graphs(ptb_ctx* ctx);
 
 static void ctx_fail(ptb_ctx* ctx, const char* what, int code) {
     if (!ctx) return;
@@ -184,6 +190,7 @@ extern "C" void ptb_destroy(ptb_ctx* ctx) {
     cudaTextureObject_t luts[6] = { ctx->F.lut_dielectric_dir_enter, ctx->F.lut_dielectric_dir_leave, ctx->F.lut_dielectric_enter,
                                     ctx->F.lut_dielectric_leave, ctx->F.lut_conductor_dir, ctx->F.lut_conductor };
     for (int i = 0; i < 6; i++) { if (luts[i]) cudaDestroyTextureObject(luts[i]); if (ctx->lut_arrays[i]) cudaFreeArray(ctx->lut_arrays[i]); }
+    drop_graphs(ctx);
     for (void* p : ctx->allocs) cudaFree(p);
     for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -227,8 +234,15 @@ static int ensure_svgf(ptb_ctx* ctx) {
     return 0;
 }
 
+static void drop_graphs(ptb_ctx* ctx) {
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
+}
+
 extern "C" int ptb_set_config(ptb_ctx* ctx, const ptb_config* config) {
     if (!ctx || !config) return PTB_E_BADARG;
+    { ptb_config incoming = *config; incoming.aov_mask |= ctx->F.config.aov_mask & 1u;
+      if (memcmp(&incoming, &ctx->F.config, sizeof(incoming)) != 0) drop_graphs(ctx); }
     if (config->num_bounces < 1 || config->num_bounces > PTB_MAX_BOUNCES - 1) return PTB_E_BADARG;
     CK(cudaSetDevice(ctx->device));
     ctx->F.config = *config;
@@ -237,13 +251,15 @@ extern "C" int ptb_set_config(ptb_ctx* ctx, const ptb_config* config) {
         ctx->F.config.aov_mask |= (1u << PTB_AOV_RADIANCE_DIRECT) | (1u << PTB_AOV_RADIANCE_INDIRECT) | (1u << PTB_AOV_ALBEDO);
         int e = ensure_svgf(ctx); if (e) return e;
     }
-    for (int k = 0; k < PTB_AOV_COUNT; k++) if (ctx->F.config.aov_mask & (1u << k)) { int e = ensure_aov(ctx, k); if (e) return e; }
+    for (int k = 0; k < PTB_AOV_COUNT; k++) if (ctx->F.config.aov_mask & (1u << k)) { if (!ctx->F.aov[k].fb) drop_graphs(ctx); int e = ensure_aov(ctx, k); if (e) return e; }
     ctx->frames_since_reset = 0;
     return 0;
 }
 
 extern "C" int ptb_set_camera(ptb_ctx* ctx, const ptb_camera* camera, const float* vp, const float* vp_prev) {
     if (!ctx || !camera) return PTB_E_BADARG;
+    if (memcmp(&ctx->F.camera, camera, sizeof(*camera)) != 0 || (vp && memcmp(ctx->F.svgf.view_projection, vp, 64) != 0) ||
+        (vp_prev && memcmp(ctx->F.svgf.view_projection_prev, vp_prev, 64) != 0)) drop_graphs(ctx);   // the parameter block is baked into captured graphs
     ctx->F.camera = *camera;
     if (vp) memcpy(ctx->F.svgf.view_projection, vp, 64);
     if (vp_prev) memcpy(ctx->F.svgf.view_projection_prev, vp_prev, 64);
@@ -416,6 +432,7 @@ extern "C" int ptb_update_instances(ptb_ctx* ctx, const void* tlas_nodes, int tl
     if (!ctx || !ctx->has_scene) return PTB_E_NOSCENE;
     if (mesh_count != ctx->mesh_capacity || tlas_node_count > 2 * mesh_count || !tlas_nodes) return PTB_E_BADARG;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->bvh_kind == 8 && ctx->F.tlas_nodes != tlas_node_count) drop_graphs(ctx);
     Frame& F = ctx->F;
     size_t node_bytes = ctx->bvh_kind == 8 ? 80 : 32;
     void* dst = ctx->bvh_kind == 8 ? (void*)F.nodes8 : (void*)F.nodes2;
@@ -484,10 +501,45 @@ extern "C" int ptb_render(ptb_ctx* ctx, int sample_index) {
           k_accumulate<<<g1d, 256, 0, st>>>(F, float(sample_index)); ctx->launches++;
       } }
     k_fold_counters<<<1, PTB_MAX_BOUNCES, 0, st>>>(F); ctx->launches++;
-    CK(cudaGetLastError());
+    if (!ctx->capturing) CK(cudaGetLastError());
     ctx->last_sample_index = sample_index;
     ctx->frames_since_reset++;
     return 0;
+}
+
+extern "C" int ptb_render_frame(ptb_ctx* ctx, int first_sample_index, int num_passes) {
+    if (!ctx || num_passes <= 0) return PTB_E_BADARG;
+    if (!ctx->has_scene) return PTB_E_NOSCENE;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->timing || ctx->stats_mode) {            // per-stage events are not captured into graphs
+        for (int i = 0; i < num_passes; i++) { int e = ptb_render(ctx, first_sample_index + i); if (e) return e; }
+        return 0;
+    }
+    for (auto& g : ctx->graphs) if (g.first == first_sample_index && g.passes == num_passes) {
+        CK(cudaGraphLaunch(g.exec, ctx->stream));
+        ctx->launches += ctx->launches_per_pass * num_passes;
+        ctx->last_sample_index = first_sample_index + num_passes - 1;
+        ctx->frames_since_reset += num_passes;
+        return 0;
+    }
+    long long before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    int e = 0;
+    for (int i = 0; i < num_passes && !e; i++) e = ptb_render(ctx, first_sample_index + i);
+    ctx->capturing = false;
+    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (e) { if (graph) cudaGraphDestroy(graph); return e; }
+    CK(ce);
+    ctx->launches_per_pass = (ctx->launches - before) / num_passes;
+    ctx->launches = before;                           // capture itself executed nothing
+    cudaGraphExec_t exec = nullptr;
+    CK(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    if (ctx->graphs.size() >= 8) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
+    ctx->graphs.push_back({ first_sample_index, num_passes, exec });
+    return ptb_render_frame(ctx, first_sample_index, num_passes);
 }
 
 extern "C" int ptb_measure_traversal(ptb_ctx* ctx, int sample_index, ptb_traversal_stats* out) {

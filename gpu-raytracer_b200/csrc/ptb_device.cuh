@@ -305,14 +305,37 @@ PTB_DI float ggx_G2(float3 wo, float3 wi, float3 wm, float ax, float ay) {
 // Kulla-Conty lookups (KullaConty.h:12-65)
 PTB_DI float remapf(float v, float a, float b, float c, float d) { return c + (v - a) / (b - a) * (d - c); }
 PTB_DI float3 fresnel_multiscatter(float3 F_avg, float E_avg) { return F_avg * F_avg * E_avg / (f3(1.0f) - F_avg * (1.0f - E_avg)); }
+// NOTE (ptxas 12.9 / sm_100a): a texture fetch whose bindless handle is NOT warp-uniform is compiled to a "waterfall" loop
+// (R2UR + BRA.U.ANY) and in that loop ptxas re-materialises the coordinates with an unpredicated MOV into the register that
+// is also the TEX destination -- lanes served in an earlier iteration get their RESULT overwritten by a coordinate whenever
+// the loop runs more than once.  The reference's kernel_material_dielectric (`(entering ? lut_enter : lut_leave).get(...)`,
+// KullaConty.h:16-35) is hit by this in the cubin built here.  We therefore never fetch through a
+// lane-dependent handle: both LUTs are fetched through their (kernel-parameter, hence uniform) handles and the result selected.
 PTB_DI float dielectric_directional_albedo(const Frame& P, float ior, float rough, float cos_theta, bool entering) {
     ior = remapf(ior, PTB_LUT_DIELECTRIC_MIN_IOR, PTB_LUT_DIELECTRIC_MAX_IOR, 0.0f, 1.0f);
     cos_theta = fabsf(cos_theta);
-    return tex3D<float>(entering ? P.lut_dielectric_dir_enter : P.lut_dielectric_dir_leave, ior, rough, cos_theta);
+    float e = tex3D<float>(P.lut_dielectric_dir_enter, ior, rough, cos_theta);
+    float l = tex3D<float>(P.lut_dielectric_dir_leave, ior, rough, cos_theta);
+    return entering ? e : l;
 }
 PTB_DI float dielectric_albedo(const Frame& P, float ior, float rough, bool entering) {
     ior = remapf(ior, PTB_LUT_DIELECTRIC_MIN_IOR, PTB_LUT_DIELECTRIC_MAX_IOR, 0.0f, 1.0f);
-    return tex2D<float>(entering ? P.lut_dielectric_enter : P.lut_dielectric_leave, ior, rough);
+    float e = tex2D<float>(P.lut_dielectric_enter, ior, rough);
+    float l = tex2D<float>(P.lut_dielectric_leave, ior, rough);
+    return entering ? e : l;
+}
+// Fetch through a per-lane texture handle (albedo textures are per material): serve one distinct handle at a time with the
+// handle broadcast from the first pending lane, so every hardware fetch sees a warp-uniform handle (see the note above).
+template <typename Fetch>
+PTB_DI float4 fetch_per_handle(cudaTextureObject_t handle, Fetch fetch) {
+    float4 r = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    bool pending = true;
+    while (pending) {
+        unsigned m = __activemask();
+        unsigned long long first = __shfl_sync(m, (unsigned long long)handle, __ffs(m) - 1);
+        if (first == (unsigned long long)handle) { r = fetch((cudaTextureObject_t)first); pending = false; }
+    }
+    return r;
 }
 PTB_DI float conductor_directional_albedo(const Frame& P, float rough, float cos_theta) { return tex2D<float>(P.lut_conductor_dir, rough, fabsf(cos_theta)); }
 PTB_DI float conductor_albedo(const Frame& P, float rough) { return tex1D<float>(P.lut_conductor, rough); }

@@ -893,15 +893,16 @@ __global__ void __launch_bounds__(256, 2) k_shade(const __grid_constant__ Frame 
                                 ray_cone_ellipse_axes(ray_direction, gn, cone_width, ax1, ax2);
                                 float2 g1 = ellipse_axis_to_gradient(tri, inv_2area, gn, hit_point, tex_coord, ax1);
                                 float2 g2 = ellipse_axis_to_gradient(tri, inv_2area, gn, hit_point, tex_coord, ax2);
-                                texel = tex2DGrad<float4>(te.tex, tex_coord.x, tex_coord.y, g1, g2);
+                                texel = fetch_per_handle(te.tex, [&](cudaTextureObject_t t) { return tex2DGrad<float4>(t, tex_coord.x, tex_coord.y, g1, g2); });
                             } else {
                                 float lod_tri = sqrtf(fabsf(tri.te1.x * tri.te2.y - tri.te2.x * tri.te1.y) * inv_2area);
                                 float lod_cone = fabsf(cone_width / dot(ray_direction, gn));
                                 float lod = log2f(lod_tri * lod_cone);
-                                texel = tex2DLod<float4>(te.tex, tex_coord.x, tex_coord.y, lod + te.lod_bias);
+                                float level = lod + te.lod_bias;
+                                texel = fetch_per_handle(te.tex, [&](cudaTextureObject_t t) { return tex2DLod<float4>(t, tex_coord.x, tex_coord.y, level); });
                             }
                         } else {
-                            texel = tex2D<float4>(te.tex, tex_coord.x, tex_coord.y);
+                            texel = fetch_per_handle(te.tex, [&](cudaTextureObject_t t) { return tex2D<float4>(t, tex_coord.x, tex_coord.y); });
                         }
                         albedo = base * f3(texel);
                     }

@@ -68,7 +68,7 @@ class PtbTraversalStats(ctypes.Structure):
 
 
 # every symbol include/ptb.h declares (tests check the built library exports exactly these)
-ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render",
+ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_render_frame",
                "ptb_measure_traversal", "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_download", "ptb_get_ray_stats", "ptb_get_stream", "ptb_export_rows",
                "ptb_assemble_rows", "ptb_debug_read", "ptb_launch_count", "ptb_set_timing", "ptb_get_stage_ms", "ptb_stage_name",
                "ptb_error_string"]
@@ -90,6 +90,7 @@ def lib():
         l.ptb_set_camera.argtypes = [vp, ctypes.POINTER(PtbCamera), vp, vp]
         l.ptb_update_instances.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
         l.ptb_render.argtypes = [vp, ci]
+        l.ptb_render_frame.argtypes = [vp, ci, ci]
         l.ptb_measure_traversal.argtypes = [vp, ci, ctypes.POINTER(PtbTraversalStats)]
         l.ptb_sync.argtypes = [vp]
         l.ptb_get_aov.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(ci)]
@@ -234,6 +235,14 @@ class Pathtracer:
     # ---- Pathtracer::render (Pathtracer.cpp:738-855)
     def render(self):
         _check(lib().ptb_render(self._ctx, int(self.sample_index)), "ptb_render")
+
+    def render_frame(self, passes):
+        """One displayed frame of the reference's `-N passes` mode: Integrator bookkeeping for a fresh accumulation
+        (sample_index 0..passes) and the whole launch sequence replayed as one CUDA graph (ptb_render_frame)."""
+        self.invalidated_gpu_config = True
+        self.update()                                   # sample_index = 0, uploads camera/config if they changed
+        _check(lib().ptb_render_frame(self._ctx, 0, int(passes) + 1), "ptb_render_frame")
+        self.sample_index = int(passes)
 
     def render_pass(self, sample_index):
         """Direct control for tests: one pass with an explicit sample index (no Integrator bookkeeping)."""

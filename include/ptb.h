@@ -137,6 +137,10 @@ int  ptb_update_instances(ptb_ctx* ctx, const void* tlas_nodes, int tlas_node_co
                           const float* transforms, const float* transforms_inv, const float* transforms_prev);
 /* Pathtracer::render() for one pass with the given sample_index (Pathtracer.cpp:738-855). Asynchronous on the ctx stream. */
 int  ptb_render(ptb_ctx* ctx, int sample_index);
+/* `num_passes` consecutive ptb_render calls (sample_index = first_sample_index ...) replayed as ONE CUDA graph: the launch
+ * sequence of a frame is static (queue sizes live in device memory), so the ~20 launches per pass cost one graph launch per
+ * frame.  Graphs are cached per (first_sample_index, num_passes) and dropped whenever camera / config / instances change. */
+int  ptb_render_frame(ptb_ctx* ctx, int first_sample_index, int num_passes);
 /* Same as ptb_render, with the instrumented trace kernels; blocks and returns the pass's traversal statistics. */
 int  ptb_measure_traversal(ptb_ctx* ctx, int sample_index, ptb_traversal_stats* out);
 /* cuStreamSynchronize equivalent */

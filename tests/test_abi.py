@@ -61,3 +61,11 @@ def test_bad_arguments_are_rejected():
     assert lib.ptb_create(ctypes.byref(ctx), 0, 0, 64, 0, 1, 8) == -1
     assert lib.ptb_create(ctypes.byref(ctx), 0, 64, 64, 2, 2, 8) == -1
     assert lib.ptb_render(None, 0) == -1
+
+
+def test_no_texture_waterfall_clobber_in_sass():
+    """ptxas 12.9 / sm_100a hazard: a texture fetch through a lane-dependent bindless handle becomes a
+    waterfall loop in which the TEX destination can be overwritten by a re-materialised coordinate.  Our kernels only fetch
+    through warp-uniform handles; this guards against a recompile re-introducing the pattern."""
+    import sass_scan
+    assert sass_scan.scan(build.build_cuda()) == []

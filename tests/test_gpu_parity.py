@@ -107,20 +107,69 @@ def test_config_switches_bit_exact(cases, flags):
     p.close(); r.close()
 
 
-def test_all_material_types_against_reference():
-    """plastic / dielectric / conductor + Kulla-Conty LUTs baked by our kernels vs the reference's."""
+def _material_scene(mat, seed=3, size=(192, 128)):
+    d = scene.procedural_scene("soup", seed=seed, width=size[0], height=size[1], detail=0.25)
+    m = d.add_material(mat)
+    for inst in d.instances[3:7]:
+        inst.material = m
+    return scene.build_blob(d, 8, rng="fallback")
+
+
+@pytest.mark.parametrize("name,mat", [
+    ("plastic", scene.Material(scene.MAT_PLASTIC, "p", diffuse=(0.2, 0.8, 0.8), roughness=0.2)),
+    ("conductor", scene.Material(scene.MAT_CONDUCTOR, "c", eta=(1.45, 0.43, 0.21), k=(1.95, 2.46, 3.27), roughness=0.3)),
+])
+def test_microfacet_materials_bit_exact(name, mat):
+    """plastic / conductor, the latter through the Kulla-Conty LUTs baked by OUR kernels: bit-identical to the reference."""
     if not ref_available():
         pytest.skip("oracle/_ref not built")
     from oracle import ref
-    blob = scene.build_blob(scene.procedural_scene("soup", seed=9, width=160, height=96, detail=0.25, all_materials=True), 8, rng="fallback")
+    blob = _material_scene(mat)
     cfg = pt.default_config(num_bounces=4, aov_mask=0x3F)
     p = pt.Pathtracer(blob, config=cfg); r = ref.Reference(blob, config=cfg)
-    p.render_frames(4); r.render_frames(4)
-    a, b = p.get_aov(0)[:, :160, :3], r.get_aov(0)[:, :160, :3]
+    p.render_frames(3); r.render_frames(3)
+    if name == "conductor":
+        a, b = p.lut_contents(), r.lut_contents()
+        assert np.array_equal(a[8704:].view(np.uint32), b[8704:].view(np.uint32))      # conductor LUTs (32x32 + 32): bit-identical
+        assert np.abs(a[:8704] - b[:8704]).max() < 5e-4                                  # dielectric LUTs: Monte-Carlo noise level
+    for k in range(6):
+        assert np.array_equal(p.get_aov(k)[:, :192].view(np.uint32), r.get_aov(k)[:, :192].view(np.uint32)), pt.AOV_NAMES[k]
     sp, sr = p.ray_stats(), r.ray_stats()
-    assert sp["shaded"][1] > 0 and sp["shaded"][2] > 0 and sp["shaded"][3] > 0
-    assert rel_l2(a, b) <= 1e-4, rel_l2(a, b)           # north-star tolerance on the HDR framebuffer
-    assert abs(int(sp["trace"].sum()) - int(sr["trace"].sum())) <= 1e-3 * int(sr["trace"].sum())
+    assert np.array_equal(sp["trace"], sr["trace"]) and np.array_equal(sp["shadow"], sr["shadow"]) and sp["shaded"][1:].sum() > 0
+    p.close(); r.close()
+
+
+def test_rough_dielectric_vs_reference_build():
+    """Rough dielectrics fetch the Kulla-Conty LUT through `(entering ? lut_enter : lut_leave)`, a lane-dependent texture handle.
+    ptxas 12.9 compiles that (in the reference's kernel_material_dielectric as built here) into a waterfall loop that overwrites
+    the fetched value with a texture COORDINATE for lanes served by an earlier iteration (tools/sass_scan.py).
+    The reference build's output for this BSDF therefore depends on which rays share a warp.  We check what is well defined:
+    our result is independent of warp composition (tile sharding regroups the rays) and agrees with the reference except on a
+    small fraction of the dielectric pixels."""
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    import sass_scan
+    from oracle import ref
+    assert any("kernel_material_dielectric" in b[0] for b in sass_scan.scan(ref.CUBIN))     # the reference cubin has the hazard
+    blob = _material_scene(scene.Material(scene.MAT_DIELECTRIC, "d", ior=1.5, roughness=0.3))
+    w = 192
+    cfg = pt.default_config(num_bounces=3)
+    p = pt.Pathtracer(blob, config=cfg); r = ref.Reference(blob, config=cfg)
+    p.render_frames(2); r.render_frames(2)
+    a, b = p.get_aov(0)[:, :w, :3], r.get_aov(0)[:, :w, :3]
+    differs = np.abs(a.astype(np.float64) - b).max(-1) > 1e-5 * (1e-3 + np.abs(b).max(-1))
+    assert differs.mean() < 0.12
+    assert abs(float(a.mean()) / float(b.mean()) - 1.0) < 0.05
+    # warp-composition independence: 2 tile shards (different ray -> warp grouping) reproduce the 1-GPU image bit for bit
+    whole = a
+    out = np.zeros_like(p.get_aov(0))
+    for rank in range(2):
+        q = pt.Pathtracer(blob, rank=rank, world=2, band_rows=4, config=cfg); q.render_frames(2)
+        img = q.get_aov(0)
+        rows = [y for y in range(img.shape[0]) if (y // 4) % 2 == rank]
+        out[rows] = img[rows]
+        q.close()
+    assert np.array_equal(out[:, :w, :3].view(np.uint32), whole.view(np.uint32))
     p.close(); r.close()
 
 
