@@ -370,10 +370,15 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(blob)
             line["cpu_bvh_build"] = cpu_bvh_build(blob)
-        print(json.dumps(line))
-    p.close()
+        print(json.dumps(line), flush=True)
+    # teardown order matters: tensors that were used on the ctx stream must die before the stream does
+    del packed, gathered, frame, host_frame, pinned
+    torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    torch.cuda.empty_cache()
+    p.close()
 
 
 if __name__ == "__main__":
