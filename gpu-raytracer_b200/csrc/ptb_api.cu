@@ -64,15 +64,16 @@ struct ptb_ctx {
     int  sm_count = 148;
     int  owned_rows = 0;
     std::vector<void*> allocs;       // everything cudaMalloc'ed, freed in ptb_destroy
+    std::vector<void*> wave_allocs;  // ray queues + framebuffer planes, re-allocated by ptb_reserve_wave
+    int wave_capacity = 1;           // pass slots a wave can carry
     std::vector<DeviceTexture> textures;
     cudaArray_t sky_array = nullptr;
     cudaArray_t lut_arrays[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     bool luts_ready = false;
     uint4* tap_hits = nullptr;
     long long launches = 0;
-    long long launches_per_pass = 0;
     bool stats_mode = false;
-    struct FrameGraph { int first, passes; cudaGraphExec_t exec; };
+    struct FrameGraph { int first, passes; cudaGraphExec_t exec; long long launches; };
     std::vector<FrameGraph> graphs;
     bool capturing = false;
     bool timing = false;
@@ -122,6 +123,41 @@ static int owned_rows_of(int height, int rank, int world, int band) {
 
 static int grid_for(const ptb_ctx* ctx, int blocks_per_sm) { return ctx->sm_count * blocks_per_sm; }
 
+// Ray queues, material/shadow queues and the per-slot framebuffer planes of every enabled AOV, for `samples` pass slots.
+template <typename T>
+static int wave_alloc(ptb_ctx* ctx, T** out, size_t count) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, (count ? count : 1) * sizeof(T)));
+    ctx->wave_allocs.push_back(p);
+    *out = static_cast<T*>(p);
+    return 0;
+}
+static int allocate_wave_storage(ptb_ctx* ctx, int samples) {
+    Frame& F = ctx->F;
+    if (samples < 1 || F.pix_bits + 1 > 30 || samples > (1 << (30 - F.pix_bits))) return PTB_E_BADARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (void* p : ctx->wave_allocs) cudaFree(p);
+    ctx->wave_allocs.clear();
+    const size_t N = (size_t)F.local_pixels * samples;
+    int e = 0;
+    for (int i = 0; i < 2; i++) {
+        e |= wave_alloc(ctx, &F.q[i].od0, N); e |= wave_alloc(ctx, &F.q[i].od1, N); e |= wave_alloc(ctx, &F.q[i].hit, N);
+        e |= wave_alloc(ctx, &F.q[i].path, N); e |= wave_alloc(ctx, &F.q[i].pix, N); e |= wave_alloc(ctx, &F.q[i].medium, N);
+    }
+    e |= wave_alloc(ctx, &F.sq.od0, N); e |= wave_alloc(ctx, &F.sq.od1, N); e |= wave_alloc(ctx, &F.sq.illum, N);
+    for (int m = 0; m < 4; m++) e |= wave_alloc(ctx, &F.matq[m], N);
+    const size_t plane = (size_t)F.pitch * F.height;
+    for (int k = 0; k < PTB_AOV_COUNT; k++) {
+        if (!(F.config.aov_mask & (1u << k))) { F.aov[k].fb = nullptr; continue; }
+        e |= wave_alloc(ctx, &F.aov[k].fb, plane * samples);
+        if (!e) CK(cudaMemsetAsync(F.aov[k].fb, 0, plane * samples * sizeof(float4), ctx->stream));
+        if (!F.aov[k].acc) { e |= dev_alloc(ctx, &F.aov[k].acc, plane); if (!e) CK(cudaMemsetAsync(F.aov[k].acc, 0, plane * sizeof(float4), ctx->stream)); }
+    }
+    if (e) return PTB_E_STATE;
+    ctx->wave_capacity = samples;
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- lifetime
 extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int rank, int world, int band_rows) {
     if (!out || width <= 0 || height <= 0 || world <= 0 || rank < 0 || rank >= world || band_rows <= 0) return PTB_E_BADARG;
@@ -152,24 +188,18 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     F.config.alpha_colour = 0.1f; F.config.alpha_moment = 0.1f; F.config.num_atrous_iterations = 6;
     F.config.sigma_z = 4.0f; F.config.sigma_n = 16.0f; F.config.sigma_l = 10.0f;
 
-    const size_t N = (size_t)F.local_pixels;
-    for (int i = 0; i < 2; i++) {
-        if (dev_alloc(ctx, &F.q[i].od0, N) || dev_alloc(ctx, &F.q[i].od1, N) || dev_alloc(ctx, &F.q[i].hit, N) ||
-            dev_alloc(ctx, &F.q[i].path, N) || dev_alloc(ctx, &F.q[i].pix, N) || dev_alloc(ctx, &F.q[i].medium, N)) { ptb_destroy(ctx); return PTB_E_STATE; }
-    }
-    if (dev_alloc(ctx, &F.sq.od0, N) || dev_alloc(ctx, &F.sq.od1, N) || dev_alloc(ctx, &F.sq.illum, N)) { ptb_destroy(ctx); return PTB_E_STATE; }
-    for (int m = 0; m < 4; m++) if (dev_alloc(ctx, &F.matq[m], N)) { ptb_destroy(ctx); return PTB_E_STATE; }
     if (dev_alloc(ctx, &F.counters, 1) || dev_alloc(ctx, &F.totals, 1) || dev_alloc(ctx, &F.trace_stats, 2)) { ptb_destroy(ctx); return PTB_E_STATE; }
     CK(cudaMemsetAsync(F.trace_stats, 0, 2 * sizeof(TraceStats), ctx->stream));
     CK(cudaMemsetAsync(F.counters, 0, sizeof(Counters), ctx->stream));
     CK(cudaMemsetAsync(F.totals, 0, sizeof(RayTotals), ctx->stream));
     const size_t pixels = (size_t)F.pitch * F.height;
+    F.fb_stride = (int)pixels;
+    F.pix_bits = 1; while ((1ull << F.pix_bits) < pixels) F.pix_bits++;
+    F.wave_samples = 1; F.first_sample = 0;
     if (dev_alloc(ctx, &F.display, pixels) || dev_alloc(ctx, &ctx->tap_hits, pixels)) { ptb_destroy(ctx); return PTB_E_STATE; }
     CK(cudaMemsetAsync(F.display, 0, pixels * sizeof(float4), ctx->stream));
-    // RADIANCE is always on (Pathtracer.cpp:267-268)
-    if (dev_alloc(ctx, &F.aov[PTB_AOV_RADIANCE].fb, pixels) || dev_alloc(ctx, &F.aov[PTB_AOV_RADIANCE].acc, pixels)) { ptb_destroy(ctx); return PTB_E_STATE; }
-    CK(cudaMemsetAsync(F.aov[PTB_AOV_RADIANCE].fb, 0, pixels * sizeof(float4), ctx->stream));
-    CK(cudaMemsetAsync(F.aov[PTB_AOV_RADIANCE].acc, 0, pixels * sizeof(float4), ctx->stream));
+    F.config.aov_mask = 1u;          // RADIANCE is always on (Pathtracer.cpp:267-268)
+    { int e = allocate_wave_storage(ctx, 1); if (e) { ptb_destroy(ctx); return e; } }
 
     CK(cudaFuncSetAttribute(k_trace8<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CK(cudaFuncSetAttribute(k_trace8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -191,6 +221,7 @@ extern "C" void ptb_destroy(ptb_ctx* ctx) {
                                     ctx->F.lut_dielectric_leave, ctx->F.lut_conductor_dir, ctx->F.lut_conductor };
     for (int i = 0; i < 6; i++) { if (luts[i]) cudaDestroyTextureObject(luts[i]); if (ctx->lut_arrays[i]) cudaFreeArray(ctx->lut_arrays[i]); }
     drop_graphs(ctx);
+    for (void* p : ctx->wave_allocs) cudaFree(p);
     for (void* p : ctx->allocs) cudaFree(p);
     for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -201,11 +232,10 @@ extern "C" void ptb_destroy(ptb_ctx* ctx) {
 static int ensure_aov(ptb_ctx* ctx, int k) {
     Frame& F = ctx->F;
     if (F.aov[k].fb) return 0;
-    const size_t pixels = (size_t)F.pitch * F.height;
-    int e = dev_alloc(ctx, &F.aov[k].fb, pixels); if (e) return e;
-    e = dev_alloc(ctx, &F.aov[k].acc, pixels); if (e) return e;
-    CK(cudaMemsetAsync(F.aov[k].fb, 0, pixels * sizeof(float4), ctx->stream));
-    CK(cudaMemsetAsync(F.aov[k].acc, 0, pixels * sizeof(float4), ctx->stream));
+    const size_t plane = (size_t)F.pitch * F.height;
+    int e = wave_alloc(ctx, &F.aov[k].fb, plane * ctx->wave_capacity); if (e) return e;
+    CK(cudaMemsetAsync(F.aov[k].fb, 0, plane * ctx->wave_capacity * sizeof(float4), ctx->stream));
+    if (!F.aov[k].acc) { e = dev_alloc(ctx, &F.aov[k].acc, plane); if (e) return e; CK(cudaMemsetAsync(F.aov[k].acc, 0, plane * sizeof(float4), ctx->stream)); }
     return 0;
 }
 
@@ -460,31 +490,32 @@ struct StageTimer {
 
 static size_t trace8_smem() { return 16 + (size_t)PTB_TLAS_STAGE_MAX_NODES * 80 + (size_t)PTB_SM_STACK * PTB_TRACE_BLOCK * sizeof(uint2); }
 
-extern "C" int ptb_render(ptb_ctx* ctx, int sample_index) {
-    if (!ctx) return PTB_E_BADARG;
-    if (!ctx->has_scene) return PTB_E_NOSCENE;
-    CK(cudaSetDevice(ctx->device));
-    const Frame& F = ctx->F;
+// One wave: `samples` consecutive passes (first_sample ...) through the whole pipeline.  The role of one or several
+// Pathtracer::render() calls (Pathtracer.cpp:738-855); asynchronous, no host<->device synchronisation.
+static int render_wave(ptb_ctx* ctx, int first_sample, int samples) {
+    if (samples < 1 || samples > ctx->wave_capacity) return PTB_E_BADARG;
+    Frame F = ctx->F;
+    F.first_sample = first_sample; F.wave_samples = samples;
+    if (F.config.enable_svgf && samples != 1) return PTB_E_STATE;   // SVGF is temporal: one pass per displayed frame
     cudaStream_t st = ctx->stream;
-    if (ctx->timing) { ctx->timed.clear(); ctx->event_used = 0; }
     const int g1d = grid_for(ctx, 8);
     const int gtrace = grid_for(ctx, PTB_TRACE_MIN_BLOCKS);
     const bool nee = ctx->has_lights && F.config.enable_next_event_estimation;
 
     k_begin_pass<<<1, 256, 0, st>>>(F); ctx->launches++;
-    { StageTimer t(ctx, ST_GENERATE); k_generate<<<g1d, 256, 0, st>>>(F, sample_index); ctx->launches++; }
+    { StageTimer t(ctx, ST_GENERATE); k_generate<<<g1d, 256, 0, st>>>(F); ctx->launches++; }
     for (int bounce = 0; bounce < F.config.num_bounces; bounce++) {
         { StageTimer t(ctx, ST_TRACE);
           if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<false, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce);
                                     else                 k_trace8<false, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce); }
           else                    k_trace2<false><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
           ctx->launches++; }
-        { StageTimer t(ctx, ST_SORT); k_sort<<<g1d, 256, 0, st>>>(F, bounce, sample_index); ctx->launches++; }
+        { StageTimer t(ctx, ST_SORT); k_sort<<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
         { StageTimer t(ctx, ST_SHADE);
-          if (ctx->has_type[0]) { k_shade<BSDFDiffuse><<<g1d, 256, 0, st>>>(F, bounce, sample_index); ctx->launches++; }
-          if (ctx->has_type[1]) { k_shade<BSDFPlastic><<<g1d, 256, 0, st>>>(F, bounce, sample_index); ctx->launches++; }
-          if (ctx->has_type[2]) { k_shade<BSDFDielectric><<<g1d, 256, 0, st>>>(F, bounce, sample_index); ctx->launches++; }
-          if (ctx->has_type[3]) { k_shade<BSDFConductor><<<g1d, 256, 0, st>>>(F, bounce, sample_index); ctx->launches++; } }
+          if (ctx->has_type[0]) { k_shade<BSDFDiffuse><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
+          if (ctx->has_type[1]) { k_shade<BSDFPlastic><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
+          if (ctx->has_type[2]) { k_shade<BSDFDielectric><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
+          if (ctx->has_type[3]) { k_shade<BSDFConductor><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; } }
         if (nee) {
             StageTimer t(ctx, ST_SHADOW);
             if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<true, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce);
@@ -493,17 +524,43 @@ extern "C" int ptb_render(ptb_ctx* ctx, int sample_index) {
             ctx->launches++;
         }
     }
-
     { StageTimer t(ctx, ST_POST);
       if (F.config.enable_svgf) {
-          int e = launch_svgf(ctx->F, st, sample_index, g1d, &ctx->launches); if (e) return e;
+          int e = launch_svgf(F, st, first_sample, g1d, &ctx->launches); if (e) return e;
       } else {
-          k_accumulate<<<g1d, 256, 0, st>>>(F, float(sample_index)); ctx->launches++;
+          k_accumulate<<<g1d, 256, 0, st>>>(F); ctx->launches++;
       } }
     k_fold_counters<<<1, PTB_MAX_BOUNCES, 0, st>>>(F); ctx->launches++;
     if (!ctx->capturing) CK(cudaGetLastError());
-    ctx->last_sample_index = sample_index;
-    ctx->frames_since_reset++;
+    ctx->last_sample_index = first_sample + samples - 1;
+    ctx->frames_since_reset += samples;
+    return 0;
+}
+
+extern "C" int ptb_render(ptb_ctx* ctx, int sample_index) {
+    if (!ctx) return PTB_E_BADARG;
+    if (!ctx->has_scene) return PTB_E_NOSCENE;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->timing) { ctx->timed.clear(); ctx->event_used = 0; }
+    return render_wave(ctx, sample_index, 1);
+}
+
+extern "C" int ptb_reserve_wave(ptb_ctx* ctx, int samples) {
+    if (!ctx) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    if (samples == ctx->wave_capacity) return 0;
+    drop_graphs(ctx);
+    return allocate_wave_storage(ctx, samples);
+}
+
+// passes [first, first + n) as waves of up to wave_capacity passes each
+static int render_passes(ptb_ctx* ctx, int first, int n) {
+    int cap = ctx->F.config.enable_svgf ? 1 : ctx->wave_capacity;
+    for (int done = 0; done < n;) {
+        int s = n - done < cap ? n - done : cap;
+        int e = render_wave(ctx, first + done, s); if (e) return e;
+        done += s;
+    }
     return 0;
 }
 
@@ -512,12 +569,12 @@ extern "C" int ptb_render_frame(ptb_ctx* ctx, int first_sample_index, int num_pa
     if (!ctx->has_scene) return PTB_E_NOSCENE;
     CK(cudaSetDevice(ctx->device));
     if (ctx->timing || ctx->stats_mode) {            // per-stage events are not captured into graphs
-        for (int i = 0; i < num_passes; i++) { int e = ptb_render(ctx, first_sample_index + i); if (e) return e; }
-        return 0;
+        if (ctx->timing) { ctx->timed.clear(); ctx->event_used = 0; }
+        return render_passes(ctx, first_sample_index, num_passes);
     }
     for (auto& g : ctx->graphs) if (g.first == first_sample_index && g.passes == num_passes) {
         CK(cudaGraphLaunch(g.exec, ctx->stream));
-        ctx->launches += ctx->launches_per_pass * num_passes;
+        ctx->launches += g.launches;
         ctx->last_sample_index = first_sample_index + num_passes - 1;
         ctx->frames_since_reset += num_passes;
         return 0;
@@ -526,19 +583,18 @@ extern "C" int ptb_render_frame(ptb_ctx* ctx, int first_sample_index, int num_pa
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     ctx->capturing = true;
-    int e = 0;
-    for (int i = 0; i < num_passes && !e; i++) e = ptb_render(ctx, first_sample_index + i);
+    int e = render_passes(ctx, first_sample_index, num_passes);
     ctx->capturing = false;
     cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
     if (e) { if (graph) cudaGraphDestroy(graph); return e; }
     CK(ce);
-    ctx->launches_per_pass = (ctx->launches - before) / num_passes;
+    long long graph_launches = ctx->launches - before;
     ctx->launches = before;                           // capture itself executed nothing
     cudaGraphExec_t exec = nullptr;
     CK(cudaGraphInstantiate(&exec, graph, 0));
     cudaGraphDestroy(graph);
     if (ctx->graphs.size() >= 8) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
-    ctx->graphs.push_back({ first_sample_index, num_passes, exec });
+    ctx->graphs.push_back({ first_sample_index, num_passes, exec, graph_launches });
     return ptb_render_frame(ctx, first_sample_index, num_passes);
 }
 

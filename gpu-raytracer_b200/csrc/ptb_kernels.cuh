@@ -31,15 +31,17 @@ PTB_DI void local_to_pixel(const Frame& P, int local, int& x, int& y) {
 }
 
 // ------------------------------------------------------------------------------------------ generate
-__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ Frame P, int sample_index) {
+__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ Frame P) {
     const RayQueue& q = P.q[0];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.local_pixels; i += gridDim.x * blockDim.x) {
-        int x, y; local_to_pixel(P, i, x, y);
+    const int total = P.local_pixels * P.wave_samples;          // slot-major: all pixels of pass slot 0, then slot 1, ...
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int slot = i / P.local_pixels;
+        int x, y; local_to_pixel(P, i - slot * P.local_pixels, x, y);
         int pixel_index = x + y * P.pitch;
-        Ray r = camera_ray(P, pixel_index, sample_index, x, y);
+        Ray r = camera_ray(P, pixel_index, P.first_sample + slot, x, y);
         q.od0[i] = make_float4(r.o.x, r.o.y, r.o.z, r.d.x);
         q.od1[i] = make_float4(r.d.y, r.d.z, 0.0f, 0.0f);
-        q.pix[i] = unsigned(pixel_index);
+        q.pix[i] = unsigned(pixel_index) | (unsigned(slot) << P.pix_bits);
     }
 }
 
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                             // unoccluded: deposit the light sample (Pathtracer.cu:183-196)
                             if (STATS) st_miss++;
                             float4 ill = P.sq.illum[ray_index];
-                            int px = __float_as_int(P.sq.od1[ray_index].w);
+                            int px = word_fb_index(P, __float_as_uint(P.sq.od1[ray_index].w));
                             float4 v = make_float4(ill.x, ill.y, ill.z, 0.0f);
                             aov_add(P, PTB_AOV_RADIANCE, px, v);
                             if (bounce == 0) aov_set(P, PTB_AOV_RADIANCE_DIRECT, px, v);
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
         if (SHADOW) {
             if (!occluded) {
                 float4 ill = P.sq.illum[ray_index];
-                int px = __float_as_int(b.w);
+                int px = word_fb_index(P, __float_as_uint(b.w));
                 float4 v = make_float4(ill.x, ill.y, ill.z, 0.0f);
                 aov_add(P, PTB_AOV_RADIANCE, px, v);
                 if (bounce == 0) aov_set(P, PTB_AOV_RADIANCE_DIRECT, px, v);
@@ -385,11 +387,11 @@ PTB_DI void svgf_set_gbuffers(const Frame& P, int x, int y, const Hit& hit, floa
 
 // ------------------------------------------------------------------------------------------ sort: terminate or classify
 // Src/CUDA/Pathtracer.cu:199-463.  Survivors are appended (by index) to their material queue.
-PTB_DI bool russian_roulette(const Frame& P, int pixel_index, int bounce, int sample_index, float3& throughput) {
+PTB_DI bool russian_roulette(const Frame& P, int pixel_index, int fbi, int bounce, int sample_index, float3& throughput) {
     if (bounce == P.config.num_bounces - 1) return true;
     if (P.config.enable_russian_roulette && bounce > 0) {
         float3 t = throughput;
-        if (P.config.enable_svgf) t *= f3(aov_get(P, PTB_AOV_ALBEDO, pixel_index));
+        if (P.config.enable_svgf) t *= f3(aov_get(P, PTB_AOV_ALBEDO, fbi));
         float survival = __saturatef(imax3(t.x, t.y, t.z));
         float r = rng2<DIM_RUSSIAN_ROULETTE>(P, pixel_index, bounce, sample_index).x;
         if (r > survival) return true;
@@ -412,7 +414,7 @@ PTB_DI void deposit(const Frame& P, int bounce, int px, float3 at_bounce0, float
     }
 }
 
-__global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, int bounce, int sample_index) {
+__global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, int bounce) {
     const RayQueue& q = P.q[bounce & 1];
     const RayQueue& qn = P.q[(bounce + 1) & 1];
     const int count = P.counters->trace[bounce];
@@ -427,7 +429,9 @@ __global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, i
             Hit hit = unpack_hit(__ldg(q.hit + index));
             float cone_angle = b.z, cone_width = b.w;
             unsigned pf = q.pix[index];
-            int pixel_index = int(pf & ~PTB_FLAGS_ALL);
+            int pixel_index = word_pixel(P, pf);
+            const int fbi = word_fb_index(P, pf);
+            const int sample_index = P.first_sample + word_slot(P, pf);
             bool allow_nee = (pf & PTB_FLAG_ALLOW_NEE) != 0;
             bool inside_medium = (pf & PTB_FLAG_INSIDE_MEDIUM) != 0;
             float4 path = bounce == 0 ? make_float4(1.0f, 1.0f, 1.0f, 0.0f) : q.path[index];
@@ -456,7 +460,7 @@ __global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, i
                     if (dist < hit.t) {
                         float3 pdf = wpdf * sigma_t * tr;
                         throughput *= sigma_s * tr / (pdf.x + pdf.y + pdf.z);
-                        if (!russian_roulette(P, pixel_index, bounce, sample_index, throughput)) {
+                        if (!russian_roulette(P, pixel_index, fbi, bounce, sample_index, throughput)) {
                             float3 dir_out = sample_henyey_greenstein(-ray_direction, g, rp.x, rp.y);
                             float3 org = f3(a.x, a.y, a.z) + dist * ray_direction;
                             if (P.config.enable_mipmapping && bounce == 0) {
@@ -467,7 +471,7 @@ __global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, i
                             sc_od0 = make_float4(org.x, org.y, org.z, dir_out.x);
                             sc_od1 = make_float4(dir_out.y, dir_out.z, cone_angle, cone_width);
                             sc_path = make_float4(throughput.x, throughput.y, throughput.z, 0.0f);
-                            sc_pix = unsigned(pixel_index) | PTB_FLAG_INSIDE_MEDIUM;
+                            sc_pix = (pf & ~PTB_FLAGS_ALL) | PTB_FLAG_INSIDE_MEDIUM;
                             sc_medium = medium_id;
                         }
                         ended = true;
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, i
 
             if (!ended && hit.triangle_id == PTB_INVALID) {            // miss: sample the sky (Pathtracer.cu:327-343)
                 float3 ill = throughput * sample_sky(P, ray_direction);
-                deposit(P, bounce, pixel_index, ill, ill);
+                deposit(P, bounce, fbi, ill, ill);
                 ended = true;
             }
             if (!ended) {
@@ -506,7 +510,7 @@ __global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, i
                     bool count_it = P.config.enable_next_event_estimation ? !allow_nee : true;
                     if (count_it) {
                         float3 ill = throughput * emission;
-                        deposit(P, bounce, pixel_index, emission, ill);
+                        deposit(P, bounce, fbi, emission, ill);
                     } else if (P.config.enable_multiple_importance_sampling) {
                         float cos_l = abs_dot(ray_direction, lgn);
                         float d2 = hit.t * hit.t;
@@ -516,17 +520,17 @@ __global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, i
                         if (pdf_is_valid(light_pdf)) {
                             float w = power_heuristic(brdf_pdf, light_pdf);
                             float3 ill = throughput * emission * w;
-                            aov_add(P, PTB_AOV_RADIANCE, pixel_index, f4(ill));
-                            if (bounce == 1) aov_add(P, PTB_AOV_RADIANCE_DIRECT, pixel_index, f4(ill));
-                            else             aov_add(P, PTB_AOV_RADIANCE_INDIRECT, pixel_index, f4(ill));
+                            aov_add(P, PTB_AOV_RADIANCE, fbi, f4(ill));
+                            if (bounce == 1) aov_add(P, PTB_AOV_RADIANCE_DIRECT, fbi, f4(ill));
+                            else             aov_add(P, PTB_AOV_RADIANCE_INDIRECT, fbi, f4(ill));
                         }
                     }
                     ended = true;
-                } else if (!russian_roulette(P, pixel_index, bounce, sample_index, throughput)) {
+                } else if (!russian_roulette(P, pixel_index, fbi, bounce, sample_index, throughput)) {
                     dest = mtype - PTB_MAT_DIFFUSE;
                     if (bounce > 0) q.path[index] = make_float4(throughput.x, throughput.y, throughput.z, path.w);  // roulette rescale, in place
                     // flags for the shade pass: only the medium bit survives (Pathtracer.cu:450-451)
-                    q.pix[index] = unsigned(pixel_index) | (medium_id != PTB_INVALID ? PTB_FLAG_INSIDE_MEDIUM : 0u);
+                    q.pix[index] = (pf & ~PTB_FLAGS_ALL) | (medium_id != PTB_INVALID ? PTB_FLAG_INSIDE_MEDIUM : 0u);
                 }
             }
         }
@@ -818,7 +822,7 @@ PTB_DI float2 ellipse_axis_to_gradient(const TriFull& t, float inv_2area, float3
 // Src/CUDA/Pathtracer.cu:465-757.  One kernel instantiation per BSDF; shadow rays and extension rays are appended
 // with warp-aggregated atomics.
 template <typename BSDF>
-__global__ void __launch_bounds__(256, 2) k_shade(const __grid_constant__ Frame P, int bounce, int sample_index) {
+__global__ void __launch_bounds__(256, 2) k_shade(const __grid_constant__ Frame P, int bounce) {
     const RayQueue& q = P.q[bounce & 1];
     const RayQueue& qn = P.q[(bounce + 1) & 1];
     const int count = P.counters->mat[BSDF::QUEUE][bounce];
@@ -836,7 +840,9 @@ __global__ void __launch_bounds__(256, 2) k_shade(const __grid_constant__ Frame 
             // not the identity (int(q / 65535.0f * 65535.0f) can be q - 1).  We compact by index, so replay it here.
             Hit hit = unpack_hit(pack_hit(unpack_hit(__ldg(q.hit + index))));
             unsigned pf = q.pix[index];
-            int pixel_index = int(pf & ~PTB_FLAGS_ALL);
+            int pixel_index = word_pixel(P, pf);
+            const int fbi = word_fb_index(P, pf);
+            const int sample_index = P.first_sample + word_slot(P, pf);
             int medium_id = (pf & PTB_FLAG_INSIDE_MEDIUM) ? q.medium[index] : PTB_INVALID;
             float3 throughput = f3(1.0f);
             if (bounce > 0) { float4 p = q.path[index]; throughput = f3(p.x, p.y, p.z); }
@@ -907,14 +913,14 @@ __global__ void __launch_bounds__(256, 2) k_shade(const __grid_constant__ Frame 
                         albedo = base * f3(texel);
                     }
                     bsdf.albedo = albedo;
-                    if (bounce == 0) aov_set(P, PTB_AOV_ALBEDO, pixel_index, f4(albedo));
+                    if (bounce == 0) aov_set(P, PTB_AOV_ALBEDO, fbi, f4(albedo));
                     bsdf.apply_albedo(P, c, throughput);
                 } else {
-                    if (bounce == 0) aov_set(P, PTB_AOV_ALBEDO, pixel_index, f4(1.0f));
+                    if (bounce == 0) aov_set(P, PTB_AOV_ALBEDO, fbi, f4(1.0f));
                 }
                 if (bounce == 0) {
-                    aov_set(P, PTB_AOV_NORMAL, pixel_index, f4(normal));
-                    aov_set(P, PTB_AOV_POSITION, pixel_index, f4(hit_point));
+                    aov_set(P, PTB_AOV_NORMAL, fbi, f4(normal));
+                    aov_set(P, PTB_AOV_POSITION, fbi, f4(hit_point));
                 }
                 if (P.config.enable_mipmapping) cone_angle -= 2.0f * curvature * fabsf(cone_width) / dot(normal, ray_direction);
 
@@ -957,7 +963,7 @@ __global__ void __launch_bounds__(256, 2) k_shade(const __grid_constant__ Frame 
                             float3 ill = throughput * bv * emission * w / light_pdf;
                             emit_shadow = true;
                             sh0 = make_float4(hp.x, hp.y, hp.z, to_light.x);
-                            sh1 = make_float4(to_light.y, to_light.z, dist, __int_as_float(pixel_index));
+                            sh1 = make_float4(to_light.y, to_light.z, dist, __uint_as_float(pf & ~PTB_FLAGS_ALL));
                             sh_ill = make_float4(ill.x, ill.y, ill.z, 0.0f);
                         }
                     }
@@ -972,7 +978,7 @@ __global__ void __launch_bounds__(256, 2) k_shade(const __grid_constant__ Frame 
                     nx0 = make_float4(org.x, org.y, org.z, dir_out.x);
                     nx1 = make_float4(dir_out.y, dir_out.z, cone_angle, cone_width);
                     nx_path = make_float4(throughput.x, throughput.y, throughput.z, pdf);
-                    nx_pix = unsigned(pixel_index) | (nee ? PTB_FLAG_ALLOW_NEE : 0u) | (medium_id != PTB_INVALID ? PTB_FLAG_INSIDE_MEDIUM : 0u);
+                    nx_pix = (pf & ~PTB_FLAGS_ALL) | (nee ? PTB_FLAG_ALLOW_NEE : 0u) | (medium_id != PTB_INVALID ? PTB_FLAG_INSIDE_MEDIUM : 0u);
                     nx_medium = medium_id;
                 }
             }
@@ -990,23 +996,26 @@ __global__ void __launch_bounds__(256, 2) k_shade(const __grid_constant__ Frame 
 // ------------------------------------------------------------------------------------------ accumulate (+ clear)
 // kernel_accumulate (Pathtracer.cu:775-796, AOV.h:35-46) fused with the framebuffer clear the reference does with
 // separate memsets (Integrator.cpp:377-383): one read-modify-write pass over HBM per enabled AOV instead of two.
-__global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ Frame P, float n) {
+__global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ Frame P) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.local_pixels; i += gridDim.x * blockDim.x) {
         int x, y; local_to_pixel(P, i, x, y);
         int px = x + y * P.pitch;
         float4 colour = f4(0.0f);
 #pragma unroll
         for (int k = 0; k < PTB_AOV_COUNT; k++) {
-            if (k == PTB_AOV_RADIANCE_DIRECT || k == PTB_AOV_RADIANCE_INDIRECT) {   // not accumulated by the reference, only cleared
-                if (P.aov[k].fb) P.aov[k].fb[px] = f4(0.0f);
-                continue;
-            }
             if (!P.aov[k].fb) continue;
-            float4 fb = P.aov[k].fb[px];
-            float4 acc;
-            if (n > 0.0f) { acc = P.aov[k].acc[px]; acc += (fb - acc) / n; } else acc = fb;
-            P.aov[k].acc[px] = acc;
-            P.aov[k].fb[px] = f4(0.0f);
+            const bool averaged = !(k == PTB_AOV_RADIANCE_DIRECT || k == PTB_AOV_RADIANCE_INDIRECT);   // those two are only cleared by the reference
+            float4 acc = averaged ? P.aov[k].acc[px] : f4(0.0f);
+            for (int s = 0; s < P.wave_samples; s++) {       // fold the slot planes in pass order: same arithmetic as one kernel_accumulate per pass
+                int fbi = s * P.fb_stride + px;
+                if (averaged) {
+                    float4 fb = P.aov[k].fb[fbi];
+                    float n = float(P.first_sample + s);
+                    if (n > 0.0f) acc += (fb - acc) / n; else acc = fb;
+                }
+                P.aov[k].fb[fbi] = f4(0.0f);
+            }
+            if (averaged) P.aov[k].acc[px] = acc;
             if (k == PTB_AOV_RADIANCE) colour = acc;
         }
         if (!isfinite(colour.x + colour.y + colour.z)) colour = make_float4(1000.0f, 0.0f, 1000.0f, 1.0f);
@@ -1021,7 +1030,7 @@ __global__ void k_begin_pass(const __grid_constant__ Frame P) {
     int* c = reinterpret_cast<int*>(P.counters);
     for (int i = threadIdx.x; i < int(sizeof(Counters) / sizeof(int)); i += blockDim.x) c[i] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) P.counters->trace[0] = P.local_pixels;
+    if (threadIdx.x == 0) P.counters->trace[0] = P.local_pixels * P.wave_samples;
 }
 // End of pass: fold the per-bounce counters into 64-bit totals (for Mrays/s).
 __global__ void k_fold_counters(const __grid_constant__ Frame P) {
@@ -1037,7 +1046,7 @@ __global__ void k_fold_counters(const __grid_constant__ Frame P) {
 // primary-hit tap for parity tests: pixel-keyed copy of the bounce-0 hits
 __global__ void k_tap_primary_hits(const __grid_constant__ Frame P, uint4* out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.local_pixels; i += gridDim.x * blockDim.x)
-        out[P.q[0].pix[i] & ~PTB_FLAGS_ALL] = P.q[0].hit[i];
+        out[word_pixel(P, P.q[0].pix[i])] = P.q[0].hit[i];                   // slot 0 of the last wave
 }
 
 // tile export / assemble for the multi-GPU gather

@@ -101,6 +101,14 @@ struct Frame {
     int width, height, pitch;
     int rank, world, band_rows;
     int local_pixels;                 // pixels this rank traces per pass
+    // A "wave" carries wave_samples consecutive passes (sample indices first_sample ...) through the pipeline at once: with
+    // 180 GB of HBM the 8 spp of a frame need not be traced one pass at a time (the reference's per-pass launches leave the late,
+    // nearly empty bounces latency bound).  Every ray carries its pass slot next to its pixel index, each slot has its own
+    // framebuffer plane, and k_accumulate folds the planes into the running mean in pass order, so the result is bit-identical
+    // to tracing the passes one after another.
+    int wave_samples, first_sample;
+    int pix_bits;                     // pixel index occupies the low pix_bits of the `pix` word, the pass slot the bits above (below the 2 flag bits)
+    int fb_stride;                    // pitch * height: distance between framebuffer planes of consecutive slots
     ptb_config config;
     ptb_camera camera;
 

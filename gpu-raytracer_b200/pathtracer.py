@@ -68,7 +68,7 @@ class PtbTraversalStats(ctypes.Structure):
 
 
 # every symbol include/ptb.h declares (tests check the built library exports exactly these)
-ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_render_frame",
+ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_reserve_wave", "ptb_render_frame",
                "ptb_measure_traversal", "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_download", "ptb_get_ray_stats", "ptb_get_stream", "ptb_export_rows",
                "ptb_assemble_rows", "ptb_debug_read", "ptb_launch_count", "ptb_set_timing", "ptb_get_stage_ms", "ptb_stage_name",
                "ptb_error_string"]
@@ -91,6 +91,7 @@ def lib():
         l.ptb_update_instances.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
         l.ptb_render.argtypes = [vp, ci]
         l.ptb_render_frame.argtypes = [vp, ci, ci]
+        l.ptb_reserve_wave.argtypes = [vp, ci]
         l.ptb_measure_traversal.argtypes = [vp, ci, ctypes.POINTER(PtbTraversalStats)]
         l.ptb_sync.argtypes = [vp]
         l.ptb_get_aov.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(ci)]
@@ -235,6 +236,10 @@ class Pathtracer:
     # ---- Pathtracer::render (Pathtracer.cpp:738-855)
     def render(self):
         _check(lib().ptb_render(self._ctx, int(self.sample_index)), "ptb_render")
+
+    def reserve_wave(self, samples):
+        """Let a wave carry `samples` passes at once (ptb_reserve_wave); results stay bit-identical to pass-by-pass tracing."""
+        _check(lib().ptb_reserve_wave(self._ctx, int(samples)), "ptb_reserve_wave")
 
     def render_frame(self, passes):
         """One displayed frame of the reference's `-N passes` mode: Integrator bookkeeping for a fresh accumulation

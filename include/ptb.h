@@ -137,6 +137,10 @@ int  ptb_update_instances(ptb_ctx* ctx, const void* tlas_nodes, int tlas_node_co
                           const float* transforms, const float* transforms_inv, const float* transforms_prev);
 /* Pathtracer::render() for one pass with the given sample_index (Pathtracer.cpp:738-855). Asynchronous on the ctx stream. */
 int  ptb_render(ptb_ctx* ctx, int sample_index);
+/* Number of pass slots a wave can carry (default 1).  With `samples` > 1, ptb_render_frame traces up to that many consecutive
+ * passes TOGETHER (every ray carries its pass slot; each slot has its own framebuffer plane; the accumulate pass folds the
+ * planes in pass order, so accumulators are bit-identical to tracing pass by pass).  Re-allocates the ray queues. */
+int  ptb_reserve_wave(ptb_ctx* ctx, int samples);
 /* `num_passes` consecutive ptb_render calls (sample_index = first_sample_index ...) replayed as ONE CUDA graph: the launch
  * sequence of a frame is static (queue sizes live in device memory), so the ~20 launches per pass cost one graph launch per
  * frame.  Graphs are cached per (first_sample_index, num_passes) and dropped whenever camera / config / instances change. */

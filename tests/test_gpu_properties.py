@@ -89,6 +89,34 @@ def test_cuda_graph_frame_replay_is_identical():
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("wave,world", [(5, 1), (3, 1), (5, 2)])
+def test_multi_pass_waves_are_bit_identical_to_pass_by_pass(wave, world):
+    """ptb_reserve_wave: several passes traced together (per-ray pass slot, per-slot framebuffer planes, ordered fold) give the
+    same accumulators, display image and ray counts as tracing the passes one after another -- also under tile sharding."""
+    d = scene.procedural_scene("atrium", seed=6, width=256, height=160, detail=0.5, all_materials=False)
+    blob = scene.build_blob(d, 8, rng="fallback")
+    cfg = pt.default_config(num_bounces=4, aov_mask=0x3F)
+    base = pt.Pathtracer(blob, config=cfg); base.render_frames(4)
+    out = np.zeros_like(base.get_aov(0)); rays = 0
+    outs = {k: np.zeros_like(out) for k in (0, 3, 4, 5)}
+    for rank in range(world):
+        q = pt.Pathtracer(blob, rank=rank, world=world, band_rows=8, config=cfg)
+        q.reserve_wave(wave)
+        q.render_frame(4); q.sync()
+        rows = [y for y in range(160) if (y // 8) % world == rank]
+        for k in outs:
+            outs[k][rows] = q.get_aov(k)[rows]
+        rays += int(q.ray_stats()["trace"].sum() + q.ray_stats()["shadow"].sum())
+        if world == 1:
+            assert np.array_equal(q.get_display().view(np.uint32), base.get_display().view(np.uint32))
+            assert not q.get_aov(0, accumulated=False).any()            # every framebuffer plane was cleared by the fold
+        q.close()
+    for k in outs:
+        assert np.array_equal(outs[k].view(np.uint32), base.get_aov(k).view(np.uint32)), pt.AOV_NAMES[k]
+    assert rays == int(base.ray_stats()["trace"].sum() + base.ray_stats()["shadow"].sum())
+    base.close()
+
+
 def test_edge_cases():
     # width not a multiple of 32 (pitch padding), one bounce, no lights, a single triangle
     d = scene.procedural_scene("soup", seed=2, width=70, height=33, detail=0.1)
