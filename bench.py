@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--detail", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--band-rows", type=int, default=8)
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="multi-GPU frame gather: fused peer-memory stores or NCCL all-gather")
     ap.add_argument("--wave", type=int, default=PASSES_PER_STEP, help="passes traced together per wave (1 = pass by pass like the reference)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -248,9 +249,31 @@ def main():
     frame = torch.empty((HEIGHT, p.screen_pitch, 4), dtype=torch.float32, device="cuda") if world > 1 else None
     host_frame = torch.empty((HEIGHT, p.screen_pitch, 4), dtype=torch.float32).pin_memory()
 
+    # ---- the per-frame gather.  "p2p": fused into the last accumulate kernel over NVLink peer memory (ptb_exchange_*, every rank
+    # ends the frame holding the whole image, no extra launches); "nccl": export -> all_gather -> assemble (3 launches + NCCL).
+    gather_mode = "none"
+    if world > 1:
+        gather_mode = args.gather
+        if gather_mode == "p2p":
+            ok = 1
+            try:
+                _, handle = p.exchange_create()
+                handles = [None] * world
+                dist.all_gather_object(handles, handle)
+                p.exchange_connect_ipc(handles)
+            except Exception as e:                      # e.g. IPC not permitted in this container: say so and use NCCL
+                print(f"[bench] rank {rank}: peer-memory exchange unavailable ({e}); using the NCCL gather", file=sys.stderr, flush=True)
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                if ok:
+                    p.exchange_disconnect()
+                gather_mode = "nccl"
+
     def one_frame(gather=True):
         p.render_frame(PASSES_PER_STEP - 1)       # sample_index 0..8 (Integrator.cpp:518-526), replayed as one CUDA graph
-        if world > 1 and gather:
+        if world > 1 and gather and gather_mode == "nccl":
             with torch.cuda.stream(stream):
                 p.export_rows(packed.data_ptr(), pt.AOV_RADIANCE)
                 dist.all_gather_into_tensor(gathered, packed)
@@ -323,13 +346,14 @@ def main():
                                  *[ctypes.c_void_p(x.data_ptr()) for x in pinned[1:]])
         p.invalidated_camera = True
         one_frame()
-        src = frame if world > 1 else None
         with torch.cuda.stream(stream):
-            if src is not None:
+            if gather_mode == "nccl":
                 if rank == 0:
-                    host_frame.copy_(src, non_blocking=True)
+                    host_frame.copy_(frame, non_blocking=True)
+            elif gather_mode == "p2p" and rank != 0:
+                pass                                    # every rank holds the frame; rank 0 is the one that hands it to the host
             else:
-                ptr, _ = p.display_device_ptr()
+                ptr = p.exchange_frame() if gather_mode == "p2p" else p.display_device_ptr()[0]
                 lib_rt.cudaMemcpyAsync(ctypes.c_void_p(host_frame.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(host_frame.numel() * 4), 2, ctypes.c_void_p(p.stream()))
         p.sync()
 
@@ -357,7 +381,7 @@ def main():
         value = rays_total / (ms_max * 1e-3) / 1e6
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "passes_per_step": PASSES_PER_STEP, "parallelism": f"tiles{world}x(bands of {args.band_rows} rows)" if world > 1 else "1 GPU", "passes_per_wave": args.wave,
+                "config": {"workload": workload, "passes_per_step": PASSES_PER_STEP, "parallelism": f"tiles{world}x(bands of {args.band_rows} rows)" if world > 1 else "1 GPU", "passes_per_wave": args.wave, "gather": gather_mode,
                            "l2": "working set (ray queues + AOVs > 400 MB per pass) exceeds the 126 MB L2", "rng_tables": blob.get("rng_source", "?"),
                            "ms_per_frame": ms_max / args.steps},
                 "rays_per_step": int(rays_total / args.steps), "clocks": clocks, "gpu_launches": int(launches),

@@ -85,7 +85,12 @@ struct ptb_ctx {
     int frames_since_reset = 0;
     std::string last_error;
     float4* svgf_ping[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };
+    // frame exchange over peer memory
+    void* xchg_block = nullptr;                       // {ExchangeControl (256 B), frame[2]} owned by this ctx
+    void* xchg_ipc_opened[PTB_MAX_PEERS] = {};        // mappings opened with cudaIpcOpenMemHandle, closed in ptb_destroy
+    unsigned xchg_frames = 0;                         // frames pushed + awaited so far (host mirror of ExchangeControl::epoch)
 };
+#define PTB_XCHG_HEADER 256
 
 static void drop_graphs(ptb_ctx* ctx);
 
@@ -214,6 +219,8 @@ extern "C" void ptb_destroy(ptb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void*& m : ctx->xchg_ipc_opened) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
+    if (ctx->xchg_block) { cudaFree(ctx->xchg_block); ctx->xchg_block = nullptr; }
     if (g_drv.ok) for (auto& t : ctx->textures) { if (t.tex) g_drv.TexObjectDestroy(t.tex); if (t.array) g_drv.MipmappedArrayDestroy(t.array); }
     if (ctx->F.sky_tex) cudaDestroyTextureObject(ctx->F.sky_tex);
     if (ctx->sky_array) cudaFreeArray(ctx->sky_array);
@@ -492,10 +499,11 @@ static size_t trace8_smem() { return 16 + (size_t)PTB_TLAS_STAGE_MAX_NODES * 80 
 
 // One wave: `samples` consecutive passes (first_sample ...) through the whole pipeline.  The role of one or several
 // Pathtracer::render() calls (Pathtracer.cpp:738-855); asynchronous, no host<->device synchronisation.
-static int render_wave(ptb_ctx* ctx, int first_sample, int samples) {
+static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = false) {
     if (samples < 1 || samples > ctx->wave_capacity) return PTB_E_BADARG;
     Frame F = ctx->F;
     F.first_sample = first_sample; F.wave_samples = samples;
+    F.xchg.push = push && F.xchg.count > 0 && !F.config.enable_svgf;
     if (F.config.enable_svgf && samples != 1) return PTB_E_STATE;   // SVGF is temporal: one pass per displayed frame
     cudaStream_t st = ctx->stream;
     const int g1d = grid_for(ctx, 8);
@@ -529,6 +537,7 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples) {
           int e = launch_svgf(F, st, first_sample, g1d, &ctx->launches); if (e) return e;
       } else {
           k_accumulate<<<g1d, 256, 0, st>>>(F); ctx->launches++;
+          if (F.xchg.push) { k_exchange_wait<<<1, 1, 0, st>>>(F); ctx->launches++; }
       } }
     k_fold_counters<<<1, PTB_MAX_BOUNCES, 0, st>>>(F); ctx->launches++;
     if (!ctx->capturing) CK(cudaGetLastError());
@@ -558,7 +567,7 @@ static int render_passes(ptb_ctx* ctx, int first, int n) {
     int cap = ctx->F.config.enable_svgf ? 1 : ctx->wave_capacity;
     for (int done = 0; done < n;) {
         int s = n - done < cap ? n - done : cap;
-        int e = render_wave(ctx, first + done, s); if (e) return e;
+        int e = render_wave(ctx, first + done, s, /*push the finished frame to the peers*/ done + s == n); if (e) return e;
         done += s;
     }
     return 0;
@@ -570,10 +579,13 @@ extern "C" int ptb_render_frame(ptb_ctx* ctx, int first_sample_index, int num_pa
     CK(cudaSetDevice(ctx->device));
     if (ctx->timing || ctx->stats_mode) {            // per-stage events are not captured into graphs
         if (ctx->timing) { ctx->timed.clear(); ctx->event_used = 0; }
-        return render_passes(ctx, first_sample_index, num_passes);
+        int e = render_passes(ctx, first_sample_index, num_passes);
+        if (!e && ctx->F.xchg.count > 0 && !ctx->F.config.enable_svgf) ctx->xchg_frames++;
+        return e;
     }
     for (auto& g : ctx->graphs) if (g.first == first_sample_index && g.passes == num_passes) {
         CK(cudaGraphLaunch(g.exec, ctx->stream));
+        if (ctx->F.xchg.count > 0 && !ctx->F.config.enable_svgf) ctx->xchg_frames++;
         ctx->launches += g.launches;
         ctx->last_sample_index = first_sample_index + num_passes - 1;
         ctx->frames_since_reset += num_passes;
@@ -598,6 +610,89 @@ extern "C" int ptb_render_frame(ptb_ctx* ctx, int first_sample_index, int num_pa
     return ptb_render_frame(ctx, first_sample_index, num_passes);
 }
 
+// ---------------------------------------------------------------------------------------------- frame exchange (peer memory)
+extern "C" int ptb_exchange_create(ptb_ctx* ctx, void** local_base, void* ipc_handle_out) {
+    if (!ctx) return PTB_E_BADARG;
+    static_assert(sizeof(ExchangeControl) <= PTB_XCHG_HEADER, "control block");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size promised by ptb.h");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->F.world > PTB_MAX_PEERS) return PTB_E_BADARG;
+    if (!ctx->xchg_block) {
+        size_t bytes = PTB_XCHG_HEADER + 2 * (size_t)ctx->F.fb_stride * sizeof(float4);
+        CK(cudaMalloc(&ctx->xchg_block, bytes));
+        CK(cudaMemset(ctx->xchg_block, 0, bytes));
+    }
+    if (local_base) *local_base = ctx->xchg_block;
+    if (ipc_handle_out) CK(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(ipc_handle_out), ctx->xchg_block));
+    return 0;
+}
+
+static int exchange_connect(ptb_ctx* ctx, void* const* bases) {
+    Frame& F = ctx->F;
+    drop_graphs(ctx);
+    for (int r = 0; r < F.world; r++) {
+        char* base = static_cast<char*>(r == F.rank ? ctx->xchg_block : bases[r]);
+        if (!base) return PTB_E_BADARG;
+        F.xchg.control[r] = reinterpret_cast<ExchangeControl*>(base);
+        F.xchg.frames[r] = reinterpret_cast<float4*>(base + PTB_XCHG_HEADER);
+    }
+    F.xchg.count = F.world;
+    F.xchg.push = 0;
+    ctx->xchg_frames = 0;
+    CK(cudaMemset(ctx->xchg_block, 0, PTB_XCHG_HEADER));
+    return 0;
+}
+
+extern "C" int ptb_exchange_connect(ptb_ctx* ctx, void* const* peer_bases) {
+    if (!ctx || !peer_bases || !ctx->xchg_block) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    for (int r = 0; r < ctx->F.world; r++) {                // peers of the same process on other devices: enable peer access
+        if (r == ctx->F.rank || !peer_bases[r]) continue;
+        cudaPointerAttributes at;
+        CK(cudaPointerGetAttributes(&at, peer_bases[r]));
+        if (at.device != ctx->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ctx_fail(ctx, "cudaDeviceEnablePeerAccess", (int)e); return (int)e; }
+            cudaGetLastError();
+        }
+    }
+    return exchange_connect(ctx, peer_bases);
+}
+
+extern "C" int ptb_exchange_connect_ipc(ptb_ctx* ctx, const void* ipc_handles) {
+    if (!ctx || !ipc_handles || !ctx->xchg_block) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    void* bases[PTB_MAX_PEERS] = {};
+    const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(ipc_handles);
+    for (int r = 0; r < ctx->F.world; r++) {
+        if (r == ctx->F.rank) continue;
+        if (!ctx->xchg_ipc_opened[r]) {
+            cudaIpcMemHandle_t hh; memcpy(&hh, &h[r], sizeof(hh));
+            CK(cudaIpcOpenMemHandle(&ctx->xchg_ipc_opened[r], hh, cudaIpcMemLazyEnablePeerAccess));
+        }
+        bases[r] = ctx->xchg_ipc_opened[r];
+    }
+    return exchange_connect(ctx, bases);
+}
+
+extern "C" int ptb_exchange_disconnect(ptb_ctx* ctx) {
+    if (!ctx) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    drop_graphs(ctx);
+    ctx->F.xchg = Exchange{};
+    ctx->xchg_frames = 0;
+    return 0;
+}
+
+extern "C" int ptb_exchange_frame(ptb_ctx* ctx, void** device_ptr, int* pitch) {
+    if (!ctx || !device_ptr) return PTB_E_BADARG;
+    if (ctx->F.xchg.count == 0 || ctx->xchg_frames == 0) return PTB_E_STATE;
+    *device_ptr = static_cast<char*>(ctx->xchg_block) + PTB_XCHG_HEADER + (size_t)((ctx->xchg_frames - 1) & 1u) * ctx->F.fb_stride * sizeof(float4);
+    if (pitch) *pitch = ctx->F.pitch;
+    return 0;
+}
+
 extern "C" int ptb_measure_traversal(ptb_ctx* ctx, int sample_index, ptb_traversal_stats* out) {
     if (!ctx || !out) return PTB_E_BADARG;
     if (!ctx->has_scene) return PTB_E_NOSCENE;
@@ -620,6 +715,11 @@ extern "C" int ptb_sync(ptb_ctx* ctx) {
     if (!ctx) return PTB_E_BADARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->F.xchg.count > 0) {
+        ExchangeControl c;
+        CK(cudaMemcpy(&c, ctx->xchg_block, sizeof(c), cudaMemcpyDeviceToHost));
+        if (c.status) { ctx->last_error = "frame exchange: a peer did not deliver its rows within 4 s"; fprintf(stderr, "[ptb] %s\n", ctx->last_error.c_str()); return PTB_E_EXCHANGE; }
+    }
     if (ctx->timing && !ctx->timed.empty()) {
         for (int i = 0; i < ST_COUNT; i++) ctx->stage_ms[i] = 0.0f;
         for (auto& t : ctx->timed) { float ms = 0.0f; cudaEventElapsedTime(&ms, t.second.first, t.second.second); ctx->stage_ms[t.first] += ms; }
@@ -740,6 +840,7 @@ extern "C" const char* ptb_error_string(int code) {
         case PTB_E_BADARG: return "bad argument";
         case PTB_E_NOSCENE: return "no scene uploaded";
         case PTB_E_STATE: return "invalid state or allocation failure";
+        case PTB_E_EXCHANGE: return "frame exchange timed out waiting for a peer";
         default: return code > 0 && code < 1000 ? cudaGetErrorString((cudaError_t)code) : "CUDA driver error";
     }
 }

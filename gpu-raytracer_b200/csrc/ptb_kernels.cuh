@@ -997,6 +997,9 @@ __global__ void __launch_bounds__(256, 2) k_shade(const __grid_constant__ Frame 
 // kernel_accumulate (Pathtracer.cu:775-796, AOV.h:35-46) fused with the framebuffer clear the reference does with
 // separate memsets (Integrator.cpp:377-383): one read-modify-write pass over HBM per enabled AOV instead of two.
 __global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ Frame P) {
+    const bool push = P.xchg.count > 0 && P.xchg.push;
+    size_t plane = 0;
+    if (push) plane = size_t(P.xchg.control[P.rank]->epoch & 1u) * size_t(P.fb_stride);   // epoch only moves in k_exchange_wait, stream-ordered before us
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.local_pixels; i += gridDim.x * blockDim.x) {
         int x, y; local_to_pixel(P, i, x, y);
         int px = x + y * P.pitch;
@@ -1020,7 +1023,48 @@ __global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ Fram
         }
         if (!isfinite(colour.x + colour.y + colour.z)) colour = make_float4(1000.0f, 0.0f, 1000.0f, 1.0f);
         P.display[px] = colour;
+        if (push) {
+            for (int r = 0; r < P.xchg.count; r++) P.xchg.frames[r][plane + px] = colour;       // NVLink stores, 16 B per lane, row-contiguous
+        }
     }
+    if (push) {
+        // release: every thread fences its peer stores, the last CTA to finish announces this rank's rows on every rank
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ExchangeControl* mine = P.xchg.control[P.rank];
+            unsigned done = atomicAdd(&mine->blocks_done, 1u);
+            if (done == gridDim.x - 1) {
+                mine->blocks_done = 0;
+                __threadfence_system();
+                const unsigned frame_no = mine->epoch + 1u;
+                for (int r = 0; r < P.xchg.count; r++) {
+                    unsigned* slot = &P.xchg.control[r]->arrivals[P.rank];
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(slot), "r"(frame_no) : "memory");
+                }
+            }
+        }
+    }
+}
+
+// Wait until every rank has stored its rows of the current frame into OUR block, then advance the epoch (which flips the
+// buffer the next frame is stored to).  One thread; bounded spin (a lost peer must not hang the GPU).
+__global__ void k_exchange_wait(const __grid_constant__ Frame P) {
+    ExchangeControl* mine = P.xchg.control[P.rank];
+    const unsigned target = mine->epoch + 1u;
+    unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        bool all = true;
+        for (int r = 0; r < P.xchg.count; r++) {
+            unsigned seen; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(&mine->arrivals[r]) : "memory");
+            all = all && int(seen - target) >= 0;
+        }
+        if (all) break;
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 4000000000ull) { mine->status = 1u; break; }
+        __nanosleep(200);
+    }
+    mine->epoch += 1u;
 }
 
 // ------------------------------------------------------------------------------------------ bookkeeping

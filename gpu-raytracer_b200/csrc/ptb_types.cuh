@@ -96,6 +96,26 @@ struct SVGFBuffers {
     float   view_projection_prev[16];
 };
 
+// Frame exchange over NVLink peer memory (multi-GPU).  Every rank owns one block {2 full frames, control words};
+// the blocks of all ranks are mapped into every rank (CUDA IPC between processes, plain peer access inside one).  The last
+// k_accumulate of a frame stores each finished pixel straight into the frame of EVERY rank -- the all-gather is fused into the
+// accumulate kernel, pixel by pixel, instead of export -> NCCL all_gather -> assemble -- then publishes its frame number in its
+// own arrival slot on every rank; k_exchange_wait spins until all slots of the local block carry the current frame number.  Frames alternate between two buffers so a fast rank never overwrites a
+// frame its peer is still reading.
+#define PTB_MAX_PEERS 16
+struct ExchangeControl {
+    unsigned arrivals[PTB_MAX_PEERS]; // slot s: number of frames whose rows rank s has finished storing into this block
+    unsigned blocks_done;             // local: CTAs of k_accumulate that finished storing
+    unsigned epoch;                   // local: frames completed
+    unsigned status;                  // local: 0 ok, 1 = wait timed out
+};
+struct Exchange {
+    int     count;                    // ranks taking part (0 = off)
+    int     push;                     // this launch is the last accumulate of a frame: store to the peers
+    float4* frames[PTB_MAX_PEERS];    // peer-mapped base of rank r's block: frame parity p at frames[r] + p * pitch * height
+    ExchangeControl* control[PTB_MAX_PEERS];
+};
+
 struct Frame {
     // film + tile ownership (rows are dealt to ranks in interleaved bands)
     int width, height, pitch;
@@ -154,4 +174,5 @@ struct Frame {
     cudaTextureObject_t lut_conductor_dir, lut_conductor;
 
     SVGFBuffers svgf;
+    Exchange xchg;
 };

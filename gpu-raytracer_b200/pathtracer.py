@@ -70,7 +70,7 @@ class PtbTraversalStats(ctypes.Structure):
 # every symbol include/ptb.h declares (tests check the built library exports exactly these)
 ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_reserve_wave", "ptb_render_frame",
                "ptb_measure_traversal", "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_download", "ptb_get_ray_stats", "ptb_get_stream", "ptb_export_rows",
-               "ptb_assemble_rows", "ptb_debug_read", "ptb_launch_count", "ptb_set_timing", "ptb_get_stage_ms", "ptb_stage_name",
+               "ptb_assemble_rows", "ptb_exchange_create", "ptb_exchange_connect", "ptb_exchange_connect_ipc", "ptb_exchange_frame", "ptb_exchange_disconnect", "ptb_debug_read", "ptb_launch_count", "ptb_set_timing", "ptb_get_stage_ms", "ptb_stage_name",
                "ptb_error_string"]
 
 _lib = None
@@ -99,6 +99,11 @@ def lib():
         l.ptb_download.argtypes = [vp, ci, ci, vp]
         l.ptb_get_ray_stats.argtypes = [vp, ctypes.POINTER(PtbRayStats), ci]
         l.ptb_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
+        l.ptb_exchange_create.argtypes = [vp, ctypes.POINTER(vp), vp]
+        l.ptb_exchange_connect.argtypes = [vp, ctypes.POINTER(vp)]
+        l.ptb_exchange_connect_ipc.argtypes = [vp, vp]
+        l.ptb_exchange_frame.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci)]
+        l.ptb_exchange_disconnect.argtypes = [vp]
         l.ptb_export_rows.argtypes = [vp, ci, vp, ctypes.POINTER(ci)]
         l.ptb_assemble_rows.argtypes = [vp, vp, ci, vp]
         l.ptb_debug_read.argtypes = [vp, ci, vp, ctypes.c_int64]
@@ -298,6 +303,35 @@ class Pathtracer:
 
     def assemble_rows(self, device_src, max_rows, device_dst):
         _check(lib().ptb_assemble_rows(self._ctx, ctypes.c_void_p(device_src), int(max_rows), ctypes.c_void_p(device_dst)), "ptb_assemble_rows")
+
+    # ---- frame exchange over peer memory (include/ptb.h: ptb_exchange_*)
+    def exchange_create(self):
+        """Allocates this rank's exchange block; returns (device base pointer, 64-byte CUDA IPC handle)."""
+        base = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _check(lib().ptb_exchange_create(self._ctx, ctypes.byref(base), handle), "ptb_exchange_create")
+        return base.value, handle.raw
+
+    def exchange_connect(self, peer_bases):
+        """Peers in this process: list of `world` device base pointers, rank-major."""
+        arr = (ctypes.c_void_p * self.world)(*[ctypes.c_void_p(b) for b in peer_bases])
+        _check(lib().ptb_exchange_connect(self._ctx, arr), "ptb_exchange_connect")
+
+    def exchange_connect_ipc(self, handles):
+        """Peers in other processes: `world` 64-byte IPC handles (bytes), rank-major."""
+        raw = b"".join(handles)
+        assert len(raw) == 64 * self.world
+        buf = ctypes.create_string_buffer(raw, len(raw))
+        _check(lib().ptb_exchange_connect_ipc(self._ctx, buf), "ptb_exchange_connect_ipc")
+
+    def exchange_disconnect(self):
+        _check(lib().ptb_exchange_disconnect(self._ctx), "ptb_exchange_disconnect")
+
+    def exchange_frame(self):
+        """Device pointer of the complete frame (pitch x height float4) delivered by the last render_frame()."""
+        p = ctypes.c_void_p()
+        _check(lib().ptb_exchange_frame(self._ctx, ctypes.byref(p), None), "ptb_exchange_frame")
+        return p.value
 
     def owned_rows(self):
         return sum(1 for y in range(self.screen_height) if (y // self.band_rows) % self.world == self.rank)

@@ -26,6 +26,7 @@ typedef struct ptb_ctx ptb_ctx;
 #define PTB_E_BADARG  (-1)
 #define PTB_E_NOSCENE (-2)
 #define PTB_E_STATE   (-3)
+#define PTB_E_EXCHANGE (-4)
 
 /* AOVType, Src/CUDA/Common.h:27-37 */
 enum { PTB_AOV_RADIANCE = 0, PTB_AOV_RADIANCE_DIRECT, PTB_AOV_RADIANCE_INDIRECT, PTB_AOV_ALBEDO, PTB_AOV_NORMAL, PTB_AOV_POSITION, PTB_AOV_COUNT };
@@ -164,6 +165,25 @@ int  ptb_export_rows(ptb_ctx* ctx, int aov_type, void* device_dst, int* owned_ro
 /* Inverse of ptb_export_rows for `world` packed tiles laid out rank-major in device_src (each max_rows x pitch float4):
  * scatters them into the full-frame image device_dst (pitch x height float4).  Used after the NCCL all-gather. */
 int  ptb_assemble_rows(ptb_ctx* ctx, const void* device_src, int max_rows, void* device_dst);
+/* Frame exchange over NVLink peer memory -- the multi-GPU gather fused into the accumulate kernel (north_star: "a final gather
+ * of the tile framebuffers").  The reference is single-GPU (Pathtracer.cpp:738-855 ends in kernel_accumulate writing the one
+ * GL surface, Pathtracer.cu:775-796); here the last accumulate of ptb_render_frame stores every finished pixel straight into
+ * the full-frame buffer of EVERY rank and the frame ends with a device-side wait for all peers, so after ptb_render_frame each
+ * rank holds the complete image -- no export / all_gather / assemble launches.
+ *   ptb_exchange_create       allocate this rank's block; returns its device base and/or its 64-byte CUDA IPC handle
+ *   ptb_exchange_connect      peers living in THIS process: world base pointers, rank-major (own entry ignored)
+ *   ptb_exchange_connect_ipc  peers in other processes: world x 64-byte IPC handles, rank-major (own entry ignored)
+ *   ptb_exchange_disconnect   stop exchanging
+ *   ptb_exchange_frame        device pointer to the complete frame (pitch x height float4) of the last ptb_render_frame; valid
+ *                             until the next-but-one ptb_render_frame (two buffers alternate); read it on the ctx stream or
+ *                             order the read before the next ptb_render_frame.
+ * Every rank must call ptb_render_frame the same number of times.  A peer that does not deliver within 4 s makes the next
+ * ptb_sync return PTB_E_EXCHANGE instead of hanging the GPU. */
+int  ptb_exchange_create(ptb_ctx* ctx, void** local_base, void* ipc_handle_out);
+int  ptb_exchange_connect(ptb_ctx* ctx, void* const* peer_bases);
+int  ptb_exchange_connect_ipc(ptb_ctx* ctx, const void* ipc_handles);
+int  ptb_exchange_frame(ptb_ctx* ctx, void** device_ptr, int* pitch);
+int  ptb_exchange_disconnect(ptb_ctx* ctx);   /* back to rank-local frames (the block stays allocated) */
 /* Debug/parity taps: copy queue state of the LAST rendered pass to host.  which: 0 = primary hits (pitch*height uint4, pixel keyed) */
 int  ptb_debug_read(ptb_ctx* ctx, int which, void* host_dst, int64_t bytes);
 /* Number of kernels this library launched since creation (bench.py's gpu_launches) */

@@ -148,3 +148,63 @@ def test_errors_are_reported_not_swallowed():
     bad = pt.default_config(num_bounces=0)
     assert lib.ptb_set_config(ctx, ctypes.byref(bad)) == -1
     lib.ptb_destroy(ctx)
+
+
+def test_peer_memory_frame_exchange_is_the_whole_frame():
+    """ptb_exchange_*: world=3 ranks (three ctxs on this GPU, blocks connected by raw pointers) render a frame each; the last
+    accumulate kernel stores every rank's rows into every rank's frame, so each rank's exchange frame == the 1-GPU frame bit for
+    bit -- with no export / all_gather / assemble.  Two frames (both buffer parities), second one with a moved camera."""
+    import ctypes
+    d = scene.procedural_scene("atrium", seed=9, width=416, height=250, detail=0.5)
+    blob = scene.build_blob(d, 8, rng="fallback")
+    cfg = pt.default_config(num_bounces=3)
+    world = 3
+    whole = pt.Pathtracer(blob, config=cfg)
+    ranks = [pt.Pathtracer(blob, rank=r, world=world, band_rows=8, config=cfg) for r in range(world)]
+    for p in ranks:
+        p.reserve_wave(5)
+    bases = [p.exchange_create()[0] for p in ranks]
+    for p in ranks:
+        p.exchange_connect(bases)
+    cam2 = np.array(blob["camera"]); cam2[0] += 0.25
+    rt = ctypes.CDLL("libcudart.so.12")
+    for frame_no, cam in enumerate([blob["camera"], cam2, blob["camera"]]):
+        whole.set_camera(cam); whole.render_frame(4); whole.sync()
+        want = whole.get_aov(0)
+        for p in ranks:                       # enqueue all three before waiting on any: each frame ends with a device-side wait for its peers
+            p.set_camera(cam); p.render_frame(4)
+        for p in ranks:
+            p.sync()
+            got = np.empty_like(want)
+            assert rt.cudaMemcpy(ctypes.c_void_p(got.ctypes.data), ctypes.c_void_p(p.exchange_frame()), ctypes.c_size_t(got.nbytes), 2) == 0
+            assert np.array_equal(got[:, :416].view(np.uint32), want[:, :416].view(np.uint32)), (frame_no, p.rank)
+    # after a disconnect a rank renders on its own again
+    ranks[0].exchange_disconnect(); ranks[0].render_frame(4); ranks[0].sync()
+    for p in ranks:
+        p.close()
+    whole.close()
+
+
+def test_peer_memory_exchange_times_out_instead_of_hanging():
+    """A peer that never delivers must not hang the GPU: the device-side wait gives up after 4 s and ptb_sync reports it."""
+    d = scene.procedural_scene("soup", seed=2, width=96, height=64, detail=0.3)
+    blob = scene.build_blob(d, 8, rng="fallback")
+    a = pt.Pathtracer(blob, rank=0, world=2, band_rows=8)
+    b = pt.Pathtracer(blob, rank=1, world=2, band_rows=8)
+    bases = [a.exchange_create()[0], b.exchange_create()[0]]
+    a.exchange_connect(bases); b.exchange_connect(bases)
+    a.render_frame(1)                         # b never renders
+    with pytest.raises(RuntimeError, match="exchange"):
+        a.sync()
+    a.close(); b.close()
+
+
+@pytest.mark.skipif(__import__("torch").cuda.device_count() < 2, reason="needs 2 GPUs (CUDA IPC between two processes)")
+def test_peer_memory_exchange_between_processes():
+    """Two processes, one GPU each, blocks connected through CUDA IPC handles: both end up with the 1-GPU frame."""
+    import subprocess, sys
+    worker = os.path.join(os.path.dirname(__file__), "_exchange_worker.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", worker], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("EXCHANGE-OK") == 2, r.stdout[-2000:]
