@@ -48,10 +48,12 @@ def build_cuda(force=False, verbose=False, defines=(), suffix=""):
     """defines/suffix build tuning variants (libptb<suffix>.so) for A/B measurements; the product is the plain libptb.so."""
     srcs, hdrs = cuda_sources()
     out = os.path.join(PKG_DIR, "csrc", f"libptb{suffix}.so")
-    if force or _stale(out, srcs + hdrs):
+    if force or _stale(out, srcs + hdrs + [os.path.join(PKG_DIR, "host", "bvh_build.cpp")]):
         cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC", "-shared",
                *[f"-D{d}" for d in defines],
-               "-I", os.path.join(REPO_ROOT, "include"), "-I", os.path.join(PKG_DIR, "csrc"), "-o", out, *srcs]
+               "-Xcompiler", "-ffp-contract=off",
+               "-I", os.path.join(REPO_ROOT, "include"), "-I", os.path.join(PKG_DIR, "csrc"), "-o", out, *srcs,
+               os.path.join(PKG_DIR, "host", "bvh_build.cpp")]          # the CPU SAH/CWBVH builder, also used inside libptb (static merge)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         log = _run(cmd)

@@ -45,8 +45,8 @@ static int load_driver_api() {
     return 0;
 }
 
-enum Stage { ST_GENERATE = 0, ST_TRACE, ST_SORT, ST_SHADE, ST_SHADOW, ST_POST, ST_COUNT };
-static const char* kStageNames[ST_COUNT] = { "generate", "trace", "sort", "shade", "shadow_trace", "accumulate_or_svgf" };
+enum Stage { ST_GENERATE = 0, ST_TRACE, ST_SORT, ST_SHADE, ST_SHADOW, ST_POST, ST_ORDER, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = { "generate", "trace", "sort", "shade", "shadow_trace", "accumulate_or_svgf", "ray_order" };
 
 struct DeviceTexture {
     CUmipmappedArray array = nullptr;
@@ -85,12 +85,35 @@ struct ptb_ctx {
     int frames_since_reset = 0;
     std::string last_error;
     float4* svgf_ping[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };
+    // static merge: identity-transform instances re-built into ONE CWBVH at upload (rebuild_static_merge)
+    bool merge_enabled = true;
+    std::vector<unsigned char> host_nodes;            // node array as uploaded by the host (for leaf walks)
+    std::vector<float4> host_tri_pos;                 // first 3 float4 of every triangle record
+    std::vector<int> host_roots;                      // roots as last given by the host
+    std::vector<int> merge_slot_root;                 // merged slot -> BLAS root (identity bit included)
+    std::vector<int> merge_slot_instance;             // merged slot -> instance index in the current TLAS leaf order
+    float4* merge_nodes = nullptr;                    // device: [host node array | merged nodes], owned
+    float4* merge_tris = nullptr;
+    int*    merge_slot_instance_dev = nullptr;
+    const float4* uploaded_nodes = nullptr;           // device copy of the host's array (kept: the fallback when nothing is merged)
     // frame exchange over peer memory
     void* xchg_block = nullptr;                       // {ExchangeControl (256 B), frame[2]} owned by this ctx
     void* xchg_ipc_opened[PTB_MAX_PEERS] = {};        // mappings opened with cudaIpcOpenMemHandle, closed in ptb_destroy
     unsigned xchg_frames = 0;                         // frames pushed + awaited so far (host mirror of ExchangeControl::epoch)
 };
 #define PTB_XCHG_HEADER 256
+
+// CPU SAH + CWBVH builder (host/bvh_build.cpp, linked into this library): used for the merged static BVH
+extern "C" {
+void* ptbh_build_triangles(const float* pos, int n, int kind, float sah_node, float sah_leaf);
+int   ptbh_node_count(void* h);
+int   ptbh_index_count(void* h);
+void  ptbh_export(void* h, void* nodes_out, int* indices_out, int node_offset, int index_offset);
+void  ptbh_free(void* h);
+}
+#ifndef PTB_DEFAULT_ORDER_BINS
+#define PTB_DEFAULT_ORDER_BINS 0
+#endif
 
 static void drop_graphs(ptb_ctx* ctx);
 
@@ -151,6 +174,8 @@ static int allocate_wave_storage(ptb_ctx* ctx, int samples) {
     }
     e |= wave_alloc(ctx, &F.sq.od0, N); e |= wave_alloc(ctx, &F.sq.od1, N); e |= wave_alloc(ctx, &F.sq.illum, N);
     for (int m = 0; m < 4; m++) e |= wave_alloc(ctx, &F.matq[m], N);
+    F.order = nullptr; F.bin_rank = nullptr; F.bin_key = nullptr;
+    if (F.order_bins > 0) { e |= wave_alloc(ctx, &F.order, N); e |= wave_alloc(ctx, &F.bin_rank, N); e |= wave_alloc(ctx, &F.bin_key, N); }   // 9 B per slot, only when ordering is on
     const size_t plane = (size_t)F.pitch * F.height;
     for (int k = 0; k < PTB_AOV_COUNT; k++) {
         if (!(F.config.aov_mask & (1u << k))) { F.aov[k].fb = nullptr; continue; }
@@ -194,6 +219,9 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     F.config.sigma_z = 4.0f; F.config.sigma_n = 16.0f; F.config.sigma_l = 10.0f;
 
     if (dev_alloc(ctx, &F.counters, 1) || dev_alloc(ctx, &F.totals, 1) || dev_alloc(ctx, &F.trace_stats, 2)) { ptb_destroy(ctx); return PTB_E_STATE; }
+    if (dev_alloc(ctx, &F.bin_counts, PTB_ORDER_MAX_BOUNCE * 2 * PTB_ORDER_MAX_BINS)) { ptb_destroy(ctx); return PTB_E_STATE; }
+    CK(cudaMemsetAsync(F.bin_counts, 0, sizeof(int) * PTB_ORDER_MAX_BOUNCE * 2 * PTB_ORDER_MAX_BINS, ctx->stream));
+    F.order_bins = PTB_DEFAULT_ORDER_BINS;
     CK(cudaMemsetAsync(F.trace_stats, 0, 2 * sizeof(TraceStats), ctx->stream));
     CK(cudaMemsetAsync(F.counters, 0, sizeof(Counters), ctx->stream));
     CK(cudaMemsetAsync(F.totals, 0, sizeof(RayTotals), ctx->stream));
@@ -221,6 +249,9 @@ extern "C" void ptb_destroy(ptb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void*& m : ctx->xchg_ipc_opened) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
     if (ctx->xchg_block) { cudaFree(ctx->xchg_block); ctx->xchg_block = nullptr; }
+    if (ctx->merge_nodes) cudaFree(ctx->merge_nodes);
+    if (ctx->merge_tris) cudaFree(ctx->merge_tris);
+    if (ctx->merge_slot_instance_dev) cudaFree(ctx->merge_slot_instance_dev);
     if (g_drv.ok) for (auto& t : ctx->textures) { if (t.tex) g_drv.TexObjectDestroy(t.tex); if (t.array) g_drv.MipmappedArrayDestroy(t.array); }
     if (ctx->F.sky_tex) cudaDestroyTextureObject(ctx->F.sky_tex);
     if (ctx->sky_array) cudaFreeArray(ctx->sky_array);
@@ -401,6 +432,193 @@ static int bake_luts(ptb_ctx* ctx) {
 }
 
 // ---------------------------------------------------------------------------------------------- scene upload
+// ---------------------------------------------------------------------------------------------- static merge
+// The reference traces a two-level hierarchy: a TLAS over instances, one BLAS per mesh (Integrator.cpp:101-283, BVH8.h:204-232).
+// Sponza is 384 instances with heavily overlapping boxes, all with identity transforms: measured on the B200, the same triangles
+// in ONE CWBVH cost 35 % less trace time with a bit-identical image (tools/gpu_flat.py).  So at upload every instance whose
+// transform is the identity (root bit 31, i.e. the ray is NOT transformed on entry -- intersections are the same float
+// operations either way) is merged: its triangles are collected by walking its BLAS leaves, one SAH/CWBVH build (the CPU
+// builder of host/bvh_build.cpp) runs over all of them, the nodes are appended to the node array in breadth-first order and the
+// triangles are stored as compact 48-byte records carrying the original triangle id + merged slot.  Rays walk the merged BVH
+// first and skip merged instances in the TLAS (PTB_ROOT_MERGED); hits report the original (mesh_id, triangle_id).
+static void collect_blas_triangles(const unsigned char* nodes, unsigned root, std::vector<int>& out) {
+    std::vector<unsigned> stack{ root };
+    while (!stack.empty()) {
+        const unsigned char* n = nodes + (size_t)stack.back() * 80; stack.pop_back();
+        unsigned imask = n[15];
+        unsigned base_child, base_tri; memcpy(&base_child, n + 16, 4); memcpy(&base_tri, n + 20, 4);
+        unsigned internal = 0;
+        for (int k = 0; k < 8; k++) {
+            unsigned meta = n[24 + k];
+            if (!meta) continue;
+            if (imask & (1u << k)) { stack.push_back(base_child + internal++); continue; }
+            unsigned count = __builtin_popcount(meta >> 5), first = meta & 31u;
+            for (unsigned t = 0; t < count; t++) out.push_back(int(base_tri + first + t));
+        }
+    }
+}
+
+static void upload_roots(ptb_ctx* ctx, std::vector<int>& device_roots) {
+    cudaMemcpyAsync((void*)ctx->F.mesh_roots, device_roots.data(), sizeof(int) * device_roots.size(), cudaMemcpyHostToDevice, ctx->stream);
+    if (ctx->merge_slot_instance_dev && !ctx->merge_slot_instance.empty())
+        cudaMemcpyAsync(ctx->merge_slot_instance_dev, ctx->merge_slot_instance.data(), sizeof(int) * ctx->merge_slot_instance.size(), cudaMemcpyHostToDevice, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);     // both sources are host vectors that may change next call
+}
+
+// The host's TLAS still lists the merged instances.  In OUR copy of it (the one rays walk) every leaf slot whose instances are
+// all merged, and every internal child whose whole subtree is, gets meta = 0 -- "empty slot" to the node test, so rays never
+// descend towards instances they already intersected through the merged BVH (imask is left alone: it drives child indexing).
+static bool prune_tlas_node(unsigned char* nodes, unsigned ni, const std::vector<char>& merged) {
+    unsigned char* n = nodes + (size_t)ni * 80;
+    unsigned imask = n[15];
+    unsigned base_child, base_tri; memcpy(&base_child, n + 16, 4); memcpy(&base_tri, n + 20, 4);
+    unsigned internal = 0; bool all = true;
+    for (int k = 0; k < 8; k++) {
+        unsigned meta = n[24 + k];
+        if (imask & (1u << k)) {
+            unsigned child = base_child + internal++;
+            if (!meta) continue;
+            if (prune_tlas_node(nodes, child, merged)) n[24 + k] = 0; else all = false;
+            continue;
+        }
+        if (!meta) continue;
+        unsigned count = __builtin_popcount(meta >> 5), first = meta & 31u;
+        bool leaf_all = true;
+        for (unsigned t = 0; t < count; t++) { unsigned inst = base_tri + first + t; if (inst >= merged.size() || !merged[inst]) leaf_all = false; }
+        if (leaf_all) n[24 + k] = 0; else all = false;
+    }
+    return all;
+}
+static int upload_pruned_tlas(ptb_ctx* ctx) {
+    Frame& F = ctx->F;
+    if (F.flat_root < 0 || !ctx->merge_nodes || F.tlas_nodes <= 0) return 0;
+    std::vector<char> merged(ctx->host_roots.size(), 0);
+    for (int i : ctx->merge_slot_instance) if (i >= 0 && (size_t)i < merged.size()) merged[i] = 1;
+    std::vector<unsigned char> tl(ctx->host_nodes.begin(), ctx->host_nodes.begin() + (size_t)F.tlas_nodes * 80);
+    bool all = prune_tlas_node(tl.data(), 0, merged);
+    int flat_all = all ? 1 : 0;
+    if (flat_all != F.flat_all) { drop_graphs(ctx); F.flat_all = flat_all; }
+    CK(cudaMemcpyAsync(ctx->merge_nodes, tl.data(), tl.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // `tl` is a host temporary
+    return 0;
+}
+
+static int rebuild_static_merge(ptb_ctx* ctx) {
+    Frame& F = ctx->F;
+    drop_graphs(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int M = (int)ctx->host_roots.size();
+    std::vector<int> slots;
+    if (ctx->merge_enabled && ctx->bvh_kind == 8)
+        for (int i = 0; i < M; i++) if ((unsigned)ctx->host_roots[i] & PTB_ROOT_IDENTITY) slots.push_back(i);
+    std::vector<int> device_roots = ctx->host_roots;
+    ctx->merge_slot_root.clear(); ctx->merge_slot_instance.clear();
+    if (ctx->merge_nodes) { cudaFree(ctx->merge_nodes); ctx->merge_nodes = nullptr; }
+    if (ctx->merge_tris) { cudaFree(ctx->merge_tris); ctx->merge_tris = nullptr; }
+    if (ctx->merge_slot_instance_dev) { cudaFree(ctx->merge_slot_instance_dev); ctx->merge_slot_instance_dev = nullptr; }
+    F.flat_root = -1; F.flat_all = 0; F.flat_node_count = 0; F.flat_tris = nullptr; F.flat_slot_instance = nullptr;
+    if (ctx->bvh_kind == 8) F.nodes8 = ctx->uploaded_nodes;
+    if (slots.empty()) { upload_roots(ctx, device_roots); return 0; }
+
+    // triangles of the merged instances
+    std::vector<float> pos; std::vector<int2> who;          // (original triangle id, merged slot)
+    std::vector<int> tris;
+    for (size_t k = 0; k < slots.size(); k++) {
+        int root = ctx->host_roots[slots[k]];
+        tris.clear();
+        collect_blas_triangles(ctx->host_nodes.data(), (unsigned)root & 0x3fffffffu, tris);
+        for (int t : tris) {
+            const float4* r = &ctx->host_tri_pos[(size_t)t * 3];
+            float3 p0 = make_float3(r[0].x, r[0].y, r[0].z), e1 = make_float3(r[0].w, r[1].x, r[1].y), e2 = make_float3(r[1].z, r[1].w, r[2].x);
+            float v[9] = { p0.x, p0.y, p0.z, p0.x + e1.x, p0.y + e1.y, p0.z + e1.z, p0.x + e2.x, p0.y + e2.y, p0.z + e2.z };
+            pos.insert(pos.end(), v, v + 9);
+            who.push_back(make_int2(t, (int)k));
+        }
+        ctx->merge_slot_root.push_back(root); ctx->merge_slot_instance.push_back(slots[k]);
+        device_roots[slots[k]] = int((unsigned)root | PTB_ROOT_MERGED);
+    }
+    const int n = (int)who.size();
+    if (n == 0) { ctx->merge_slot_root.clear(); ctx->merge_slot_instance.clear(); upload_roots(ctx, ctx->host_roots); return 0; }
+    void* h = ptbh_build_triangles(pos.data(), n, 8, 4.0f, 1.0f);
+    if (!h) return PTB_E_STATE;
+    const int nm = ptbh_node_count(h);
+    std::vector<unsigned char> dfs((size_t)nm * 80), bfs((size_t)nm * 80);
+    std::vector<int> order((size_t)ptbh_index_count(h));
+    ptbh_export(h, dfs.data(), order.data(), 0, 0);
+    ptbh_free(h);
+    // breadth-first re-layout (children of a node stay contiguous and in slot order); child indices become global
+    const int base = ctx->node_count;
+    {
+        std::vector<int> queue{ 0 }; queue.reserve(nm);
+        int next = 1;
+        for (size_t qi = 0; qi < queue.size(); qi++) {
+            const unsigned char* src = dfs.data() + (size_t)queue[qi] * 80;
+            unsigned char* dst = bfs.data() + qi * 80;
+            memcpy(dst, src, 80);
+            unsigned old_base; memcpy(&old_base, src + 16, 4);
+            int kids = __builtin_popcount((unsigned)src[15]);
+            unsigned new_base = (unsigned)(base + next);
+            memcpy(dst + 16, &new_base, 4);
+            for (int c = 0; c < kids; c++) queue.push_back((int)old_base + c);
+            next += kids;
+        }
+    }
+    std::vector<float4> flat((size_t)n * 3);
+    for (int j = 0; j < n; j++) {
+        int src = order[j];
+        const float4* r = &ctx->host_tri_pos[(size_t)who[src].x * 3];
+        flat[(size_t)j * 3 + 0] = r[0]; flat[(size_t)j * 3 + 1] = r[1];
+        float id_bits, slot_bits; memcpy(&id_bits, &who[src].x, 4); memcpy(&slot_bits, &who[src].y, 4);
+        flat[(size_t)j * 3 + 2] = make_float4(r[2].x, id_bits, slot_bits, 0.0f);
+    }
+    CK(cudaMalloc(&ctx->merge_nodes, ((size_t)base + nm) * 80));
+    CK(cudaMemcpyAsync(ctx->merge_nodes, ctx->uploaded_nodes, (size_t)base * 80, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ctx->merge_nodes) + (size_t)base * 80, bfs.data(), (size_t)nm * 80, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMalloc(&ctx->merge_tris, flat.size() * sizeof(float4)));
+    CK(cudaMemcpyAsync(ctx->merge_tris, flat.data(), flat.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMalloc(&ctx->merge_slot_instance_dev, sizeof(int) * slots.size()));
+    F.nodes8 = ctx->merge_nodes;
+    F.flat_root = base; F.flat_node_count = nm; F.flat_all = (int)slots.size() == M ? 1 : 0;
+    F.flat_tris = ctx->merge_tris; F.flat_slot_instance = ctx->merge_slot_instance_dev;
+    upload_roots(ctx, device_roots);
+    return upload_pruned_tlas(ctx);
+}
+
+// New roots from the host (TLAS leaf order may have changed): keep the merged BVH if it still covers exactly the identity
+// instances, only refreshing slot -> instance; otherwise rebuild it.
+static int apply_roots(ptb_ctx* ctx, const int32_t* roots, int mesh_count) {
+    ctx->host_roots.assign(roots, roots + mesh_count);
+    if (ctx->bvh_kind != 8) { std::vector<int> r = ctx->host_roots; upload_roots(ctx, r); return 0; }
+    std::vector<int> ident;
+    for (int i = 0; i < mesh_count; i++) if ((unsigned)roots[i] & PTB_ROOT_IDENTITY) ident.push_back(i);
+    bool same = ctx->merge_enabled && ident.size() == ctx->merge_slot_root.size();
+    std::vector<int> slot_instance(ctx->merge_slot_root.size(), -1);
+    if (same) {
+        std::vector<char> taken(ident.size(), 0);
+        for (size_t k = 0; k < slot_instance.size() && same; k++) {
+            size_t j = k < ident.size() && !taken[k] && roots[ident[k]] == ctx->merge_slot_root[k] ? k : 0;    // common case: order unchanged
+            if (!(j == k && roots[ident[j]] == ctx->merge_slot_root[k] && !taken[j]))
+                for (j = 0; j < ident.size(); j++) if (!taken[j] && roots[ident[j]] == ctx->merge_slot_root[k]) break;
+            if (j == ident.size()) { same = false; break; }
+            taken[j] = 1; slot_instance[k] = ident[j];
+        }
+    }
+    if (!same) return rebuild_static_merge(ctx);
+    ctx->merge_slot_instance = slot_instance;
+    std::vector<int> device_roots = ctx->host_roots;
+    for (int i : slot_instance) device_roots[i] = int((unsigned)device_roots[i] | PTB_ROOT_MERGED);
+    upload_roots(ctx, device_roots);
+    return upload_pruned_tlas(ctx);
+}
+
+extern "C" int ptb_set_static_merge(ptb_ctx* ctx, int enabled) {
+    if (!ctx) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    if ((enabled != 0) == ctx->merge_enabled) return 0;
+    ctx->merge_enabled = enabled != 0;
+    return ctx->has_scene ? rebuild_static_merge(ctx) : 0;
+}
+
 extern "C" int ptb_upload_scene(ptb_ctx* ctx, const ptb_scene* s) {
     if (!ctx || !s) return PTB_E_BADARG;
     if (ctx->has_scene) return PTB_E_STATE;     // one scene per ctx (create a new ctx to switch scenes)
@@ -412,8 +630,16 @@ extern "C" int ptb_upload_scene(ptb_ctx* ctx, const ptb_scene* s) {
     int e = 0;
     e |= dev_upload<float4>(ctx, &F.triangles, s->triangles, (size_t)s->triangle_count * 6);
     ctx->bvh_kind = s->bvh_kind; ctx->node_count = s->bvh_node_count;
-    if (s->bvh_kind == 8) e |= dev_upload<float4>(ctx, &F.nodes8, s->bvh_nodes, (size_t)s->bvh_node_count * 5);
+    if (s->bvh_kind == 8) { e |= dev_upload<float4>(ctx, &F.nodes8, s->bvh_nodes, (size_t)s->bvh_node_count * 5); ctx->uploaded_nodes = F.nodes8; }
     else                  e |= dev_upload<float4>(ctx, &F.nodes2, s->bvh_nodes, (size_t)s->bvh_node_count * 2);
+    F.flat_root = -1;
+    if (s->bvh_kind == 8) {
+        const unsigned char* nb = static_cast<const unsigned char*>(s->bvh_nodes);
+        ctx->host_nodes.assign(nb, nb + (size_t)s->bvh_node_count * 80);
+        ctx->host_tri_pos.resize((size_t)s->triangle_count * 3);
+        const float4* tr = static_cast<const float4*>(s->triangles);
+        for (int t = 0; t < s->triangle_count; t++) for (int k = 0; k < 3; k++) ctx->host_tri_pos[(size_t)t * 3 + k] = tr[(size_t)t * 6 + k];
+    }
     F.tlas_nodes = s->bvh_kind == 8 ? s->tlas_node_count : 0;
     ctx->mesh_capacity = s->mesh_count;
     e |= dev_upload<int>(ctx, &F.mesh_roots, s->mesh_bvh_root_indices, s->mesh_count);
@@ -459,6 +685,8 @@ extern "C" int ptb_upload_scene(ptb_ctx* ctx, const ptb_scene* s) {
     F.sky_scale = s->sky_scale;
 
     ctx->has_scene = true;
+    ctx->host_roots.assign(s->mesh_bvh_root_indices, s->mesh_bvh_root_indices + s->mesh_count);
+    e = rebuild_static_merge(ctx); if (e) return e;
     if (ctx->has_type[2] || ctx->has_type[3]) { e = bake_luts(ctx); if (e) return e; }
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -474,8 +702,14 @@ extern "C" int ptb_update_instances(ptb_ctx* ctx, const void* tlas_nodes, int tl
     size_t node_bytes = ctx->bvh_kind == 8 ? 80 : 32;
     void* dst = ctx->bvh_kind == 8 ? (void*)F.nodes8 : (void*)F.nodes2;
     CK(cudaMemcpyAsync(dst, tlas_nodes, node_bytes * tlas_node_count, cudaMemcpyHostToDevice, ctx->stream));
-    if (ctx->bvh_kind == 8) F.tlas_nodes = tlas_node_count;
-    if (roots) CK(cudaMemcpyAsync((void*)F.mesh_roots, roots, sizeof(int) * mesh_count, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->bvh_kind == 8 && ctx->uploaded_nodes != F.nodes8)      // keep the un-merged copy current as well
+        CK(cudaMemcpyAsync((void*)ctx->uploaded_nodes, tlas_nodes, node_bytes * tlas_node_count, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->bvh_kind == 8) {
+        F.tlas_nodes = tlas_node_count;
+        memcpy(ctx->host_nodes.data(), tlas_nodes, node_bytes * tlas_node_count);
+    }
+    if (roots) { int re = apply_roots(ctx, roots, mesh_count); if (re) return re; }
+    else       { int re = upload_pruned_tlas(ctx); if (re) return re; }
     if (material_ids) CK(cudaMemcpyAsync((void*)F.mesh_material_ids, material_ids, sizeof(int) * mesh_count, cudaMemcpyHostToDevice, ctx->stream));
     if (xf) CK(cudaMemcpyAsync((void*)F.mesh_transforms, xf, 48 * (size_t)mesh_count, cudaMemcpyHostToDevice, ctx->stream));
     if (xf_inv) CK(cudaMemcpyAsync((void*)F.mesh_transforms_inv, xf_inv, 48 * (size_t)mesh_count, cudaMemcpyHostToDevice, ctx->stream));
@@ -513,9 +747,14 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
     k_begin_pass<<<1, 256, 0, st>>>(F); ctx->launches++;
     { StageTimer t(ctx, ST_GENERATE); k_generate<<<g1d, 256, 0, st>>>(F); ctx->launches++; }
     for (int bounce = 0; bounce < F.config.num_bounces; bounce++) {
+        const bool ordered = F.order_bins > 0 && ctx->bvh_kind == 8 && bounce < PTB_ORDER_MAX_BOUNCE;
+        const unsigned* order_c = ordered && bounce > 0 ? F.order : nullptr;       // primary rays are coherent as generated
+        const unsigned* order_s = ordered ? F.order : nullptr;
+        if (order_c) { StageTimer t(ctx, ST_ORDER);
+          k_bin_count<false><<<g1d, 256, 0, st>>>(F, bounce); k_bin_scatter<false><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches += 2; }
         { StageTimer t(ctx, ST_TRACE);
-          if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<false, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce);
-                                    else                 k_trace8<false, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce); }
+          if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<false, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order_c);
+                                    else                 k_trace8<false, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order_c); }
           else                    k_trace2<false><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
           ctx->launches++; }
         { StageTimer t(ctx, ST_SORT); k_sort<<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
@@ -524,10 +763,12 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
           if (ctx->has_type[1]) { k_shade<BSDFPlastic><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
           if (ctx->has_type[2]) { k_shade<BSDFDielectric><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
           if (ctx->has_type[3]) { k_shade<BSDFConductor><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; } }
+        if (nee && order_s) { StageTimer t(ctx, ST_ORDER);
+          k_bin_count<true><<<g1d, 256, 0, st>>>(F, bounce); k_bin_scatter<true><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches += 2; }
         if (nee) {
             StageTimer t(ctx, ST_SHADOW);
-            if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<true, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce);
-                                      else                 k_trace8<true, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce); }
+            if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<true, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order_s);
+                                      else                 k_trace8<true, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order_s); }
             else                    k_trace2<true><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
             ctx->launches++;
         }
@@ -552,6 +793,15 @@ extern "C" int ptb_render(ptb_ctx* ctx, int sample_index) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->timing) { ctx->timed.clear(); ctx->event_used = 0; }
     return render_wave(ctx, sample_index, 1);
+}
+
+extern "C" int ptb_set_ray_ordering(ptb_ctx* ctx, int bins) {
+    if (!ctx || !(bins == 0 || bins == 8 || bins == 64)) return PTB_E_BADARG;
+    if (bins != ctx->F.order_bins) {
+        drop_graphs(ctx); ctx->F.order_bins = bins;
+        if (bins > 0 && !ctx->F.order) return allocate_wave_storage(ctx, ctx->wave_capacity);
+    }
+    return 0;
 }
 
 extern "C" int ptb_reserve_wave(ptb_ctx* ctx, int samples) {

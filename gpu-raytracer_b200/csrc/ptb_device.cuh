@@ -115,6 +115,13 @@ PTB_DI TriPos load_tri_pos(const Frame& P, int id) {
     TriPos r; r.p0 = f3(a.x, a.y, a.z); r.e1 = f3(a.w, b.x, b.y); r.e2 = f3(b.z, b.w, c.x);
     return r;
 }
+// merged static BVH: compact 48-byte records, remap in the spare words
+PTB_DI TriPos load_tri_pos_flat(const Frame& P, int id, float4& c) {
+    const float4* t = P.flat_tris + 3 * size_t(id);
+    float4 a = __ldg(t), b = __ldg(t + 1); c = __ldg(t + 2);
+    TriPos r; r.p0 = f3(a.x, a.y, a.z); r.e1 = f3(a.w, b.x, b.y); r.e2 = f3(b.z, b.w, c.x);
+    return r;
+}
 struct TriFull { float3 p0, e1, e2, n0, ne1, ne2; float2 t0, te1, te2; };
 PTB_DI TriFull load_tri_full(const Frame& P, int id) {
     const float4* t = P.triangles + 6 * size_t(id);
@@ -139,7 +146,10 @@ PTB_DI Hit unpack_hit(uint4 w) {
 
 // Moeller-Trumbore, closest hit (Triangle.h:148-174)
 PTB_DI void intersect_triangle(const Frame& P, int mesh_id, int tri_id, const Ray& ray, Hit& hit) {
-    TriPos tr = load_tri_pos(P, tri_id);
+    float4 c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const bool flat = mesh_id == PTB_FLAT_MESH;
+    TriPos tr = flat ? load_tri_pos_flat(P, tri_id, c) : load_tri_pos(P, tri_id);
+    if (flat) { tri_id = __float_as_int(c.y); mesh_id = -(2 + __float_as_int(c.z)); }   // original triangle id; slot resolved when the hit is stored
     float3 h = cross(ray.d, tr.e2);
     float a = dot(tr.e1, h);
     float f = 1.0f / a;
@@ -155,8 +165,9 @@ PTB_DI void intersect_triangle(const Frame& P, int mesh_id, int tri_id, const Ra
     }
 }
 // any hit (Triangle.h:176-198)
-PTB_DI bool occludes_triangle(const Frame& P, int tri_id, const Ray& ray, float max_distance) {
-    TriPos tr = load_tri_pos(P, tri_id);
+PTB_DI bool occludes_triangle(const Frame& P, int mesh_id, int tri_id, const Ray& ray, float max_distance) {
+    float4 c;
+    TriPos tr = mesh_id == PTB_FLAT_MESH ? load_tri_pos_flat(P, tri_id, c) : load_tri_pos(P, tri_id);
     float3 h = cross(ray.d, tr.e2);
     float a = dot(tr.e1, h);
     float f = 1.0f / a;

@@ -17,9 +17,18 @@
 #define PTB_STACK_TOTAL 32                // BVH_STACK_SIZE, Common.h:104
 #define PTB_LOCAL_STACK (PTB_STACK_TOTAL - PTB_SM_STACK)
 #define PTB_TLAS_STAGE_MAX_NODES 256      // up to 20 KB of TLAS nodes bulk-copied (TMA) into shared memory per CTA
+#ifndef PTB_DYNFETCH_ND
 #define PTB_DYNFETCH_ND 4                 // dynamic fetch heuristic, Ylitie et al. 2017 section 4.4 (BVH8.h:109-111)
+#endif
+#ifndef PTB_DYNFETCH_NW
 #define PTB_DYNFETCH_NW 16
+#endif
+#ifndef PTB_POSTPONE_DIVISOR
 #define PTB_POSTPONE_DIVISOR 5            // triangle postponing threshold (BVH8.h:12-15)
+#endif
+#ifndef PTB_TILED_GENERATE
+#define PTB_TILED_GENERATE 1              // primary rays enumerated so that a warp covers an 8x4 pixel tile (not a 32x1 strip)
+#endif
 
 // ------------------------------------------------------------------------------------------ tile mapping
 // local index -> global pixel: rows are dealt to ranks in interleaved bands of band_rows rows.
@@ -30,19 +39,104 @@ PTB_DI void local_to_pixel(const Frame& P, int local, int& x, int& y) {
     y = (band * P.world + P.rank) * P.band_rows + (row - band * P.band_rows);
 }
 
+// Enumeration order of the primary rays: same pixel set as local_to_pixel, but consecutive groups of 32 indices cover an
+// 8x4 pixel tile, so a warp's rays (and every later bounce spawned from them: queue order is inherited) start out spatially
+// compact.  Purely a scheduling choice: pixel_index, the RNG key, is unchanged.
+PTB_DI void generate_order_to_pixel(const Frame& P, int local, int& x, int& y) {
+    const int band_px = P.band_rows * P.width;
+    int band = local / band_px;
+    int j = local - band * band_px;
+    int y0 = (band * P.world + P.rank) * P.band_rows;
+    int rows = min(P.band_rows, P.height - y0);
+    int row, xx;
+    if (((P.width & 7) | (rows & 3)) == 0) {
+        int tile = j >> 5, t = j & 31;
+        int tiles_x = P.width >> 3;
+        int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        xx = tx * 8 + (t & 7); row = ty * 4 + (t >> 3);
+    } else {
+        row = j / P.width; xx = j - row * P.width;
+    }
+    x = xx; y = y0 + row;
+}
+
 // ------------------------------------------------------------------------------------------ generate
 __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ Frame P) {
     const RayQueue& q = P.q[0];
     const int total = P.local_pixels * P.wave_samples;          // slot-major: all pixels of pass slot 0, then slot 1, ...
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int slot = i / P.local_pixels;
-        int x, y; local_to_pixel(P, i - slot * P.local_pixels, x, y);
+        int x, y;
+#if PTB_TILED_GENERATE
+        generate_order_to_pixel(P, i - slot * P.local_pixels, x, y);
+#else
+        local_to_pixel(P, i - slot * P.local_pixels, x, y);
+#endif
         int pixel_index = x + y * P.pitch;
         Ray r = camera_ray(P, pixel_index, P.first_sample + slot, x, y);
         q.od0[i] = make_float4(r.o.x, r.o.y, r.o.z, r.d.x);
         q.od1[i] = make_float4(r.d.y, r.d.z, 0.0f, 0.0f);
         q.pix[i] = unsigned(pixel_index) | (unsigned(slot) << P.pix_bits);
     }
+}
+
+// ------------------------------------------------------------------------------------------ ray ordering
+// Secondary and shadow rays leave k_shade in pixel order: a warp's 32 rays start close together but point anywhere, and the
+// warp-synchronous traversal then runs at half occupancy of its lanes (ncu: 15.9 of 32 threads active on shadow rays vs 25.5 on
+// primary rays).  Before such a queue is traced it is counting-sorted by DIRECTION BIN (8 octants or 8x8 octahedral cells) --
+// inside a bin the pixel order survives, so a warp gets rays that start close together AND point the same way.  The sort only
+// produces a 4-byte index per ray (`order`), the 48-byte rays stay where they are; the reference has no such step (its
+// kernel_trace_* consume the queues in emission order, Pathtracer.cu:165-197).  Results do not depend on the order rays are traced in.
+PTB_DI unsigned direction_bin(const float3& d, int bins) {
+    if (bins <= 8) return (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    float inv = 1.0f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));
+    float u = d.x * inv, v = d.y * inv;
+    if (d.z < 0.0f) {
+        float uu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f);
+        float vv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f);
+        u = uu; v = vv;
+    }
+    int iu = min(7, max(0, int((u * 0.5f + 0.5f) * 8.0f)));
+    int iv = min(7, max(0, int((v * 0.5f + 0.5f) * 8.0f)));
+    return unsigned(iv * 8 + iu);
+}
+PTB_DI int* bin_row(const Frame& P, int bounce, bool shadow) { return P.bin_counts + ((bounce * 2 + (shadow ? 1 : 0)) * PTB_ORDER_MAX_BINS); }
+
+// pass 1: bin of every ray + its rank inside the bin (CTA-aggregated: one global atomic per bin per 256 rays)
+template <bool SHADOW>
+__global__ void __launch_bounds__(256) k_bin_count(const __grid_constant__ Frame P, int bounce) {
+    __shared__ int s_cnt[PTB_ORDER_MAX_BINS];
+    __shared__ int s_base[PTB_ORDER_MAX_BINS];
+    const int count = SHADOW ? P.counters->shadow[bounce] : P.counters->trace[bounce];
+    const float4* od0 = SHADOW ? P.sq.od0 : P.q[bounce & 1].od0;
+    const float4* od1 = SHADOW ? P.sq.od1 : P.q[bounce & 1].od1;
+    int* row = bin_row(P, bounce, SHADOW);
+    for (int start = blockIdx.x * blockDim.x; start < count; start += gridDim.x * blockDim.x) {    // CTA-uniform trip count
+        if (threadIdx.x < PTB_ORDER_MAX_BINS) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        int i = start + threadIdx.x;
+        unsigned key = 0; int local = 0;
+        if (i < count) {
+            float4 a = od0[i], b = od1[i];
+            key = direction_bin(f3(a.w, b.x, b.y), P.order_bins);
+            local = atomicAdd(&s_cnt[key], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < PTB_ORDER_MAX_BINS && s_cnt[threadIdx.x] > 0) s_base[threadIdx.x] = atomicAdd(&row[threadIdx.x], s_cnt[threadIdx.x]);
+        __syncthreads();
+        if (i < count) { P.bin_key[i] = (unsigned char)key; P.bin_rank[i] = unsigned(s_base[key] + local); }
+    }
+}
+// pass 2: order[bin start + rank] = ray index
+template <bool SHADOW>
+__global__ void __launch_bounds__(256) k_bin_scatter(const __grid_constant__ Frame P, int bounce) {
+    __shared__ int s_start[PTB_ORDER_MAX_BINS];
+    const int count = SHADOW ? P.counters->shadow[bounce] : P.counters->trace[bounce];
+    const int* row = bin_row(P, bounce, SHADOW);
+    if (threadIdx.x == 0) { int acc = 0; for (int b = 0; b < PTB_ORDER_MAX_BINS; b++) { s_start[b] = acc; acc += row[b]; } }
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        P.order[unsigned(s_start[P.bin_key[i]]) + P.bin_rank[i]] = unsigned(i);
 }
 
 // ------------------------------------------------------------------------------------------ TMA staging of the TLAS
@@ -74,7 +168,8 @@ PTB_DI void stage_tlas_nodes(float4* dst, const float4* src, unsigned bytes, uns
 // triangle groups, octant-ordered child pops, TLAS->BLAS instancing, triangle postponing), restructured so that all
 // ballots are taken in uniform control flow instead of sampling __activemask().
 struct TraceShared {
-    const float4* tlas;     // staged TLAS nodes in shared memory
+    const float4* tlas;     // staged nodes in shared memory
+    unsigned      stage_base; // node index of the first staged node
     int           staged;   // number of staged nodes
     uint2*        stack;    // PTB_SM_STACK x blockDim entries, strided by blockDim (conflict free)
 };
@@ -91,15 +186,19 @@ PTB_DI uint2 stack_pop(const TraceShared& S, const uint2* local, int& sp) {
 // STATS = true additionally counts node visits / triangle tests / instance transforms per ray kind (roofline accounting:
 // algorithmic bytes = 80 B per node + 48 B per triangle + 48 B per instance transform + the ray/hit streams).
 template <bool SHADOW, bool STATS>
-__global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace8(const __grid_constant__ Frame P, int bounce) {
+__global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace8(const __grid_constant__ Frame P, int bounce, const unsigned* __restrict__ order) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw);
     float4* tlas_sm = reinterpret_cast<float4*>(smem_raw + 16);
     TraceShared S;
-    S.staged = min(P.tlas_nodes, PTB_TLAS_STAGE_MAX_NODES);
+    // staged in shared memory: the TLAS, or -- when every instance is merged and the TLAS is never walked -- the top levels of
+    // the merged BVH (breadth-first layout, so the first 256 nodes are its first ~3 levels: every ray visits several of them)
+    const bool flat_only = P.flat_root >= 0 && P.flat_all;
+    S.stage_base = flat_only ? unsigned(P.flat_root) : 0u;
+    S.staged = flat_only ? min(P.flat_node_count, PTB_TLAS_STAGE_MAX_NODES) : min(P.tlas_nodes, PTB_TLAS_STAGE_MAX_NODES);
     S.tlas = tlas_sm;
     S.stack = reinterpret_cast<uint2*>(smem_raw + 16 + size_t(PTB_TLAS_STAGE_MAX_NODES) * 80);
-    stage_tlas_nodes(tlas_sm, P.nodes8, unsigned(S.staged) * 80u, bar);
+    stage_tlas_nodes(tlas_sm, P.nodes8 + 5 * size_t(S.stage_base), unsigned(S.staged) * 80u, bar);
 
     const int count = SHADOW ? P.counters->shadow[bounce] : P.counters->trace[bounce];
     int* retired = SHADOW ? &P.counters->retired_shadow[bounce] : &P.counters->retired[bounce];
@@ -129,13 +228,22 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
             if (!live && !exhausted) {
                 ray_index = base + __popc(idle & ((1u << lane) - 1u));
                 if (ray_index < count) {
+                    if (order) ray_index = int(order[ray_index]);          // direction-binned order (k_bin_scatter)
                     float4 a, b;
                     if (SHADOW) { a = P.sq.od0[ray_index]; b = P.sq.od1[ray_index]; hit.t = b.z; }
                     else        { a = q.od0[ray_index];    b = q.od1[ray_index];    hit.t = PTB_INF; hit.triangle_id = PTB_INVALID; }
                     ray.o = f3(a.x, a.y, a.z); ray.d = f3(a.w, b.x, b.y);
                     oct4 = ray_octant_inv4(ray.d);
-                    cur = make_uint2(0u, 0x80000000u);
-                    sp = 0; tlas_sp = PTB_INVALID; live = true;
+                    sp = 0; live = true;
+                    if (P.flat_root >= 0) {
+                        // merged static BVH first (it sets a tight hit.t early); the TLAS root waits on the stack for what is not merged
+                        if (!P.flat_all) stack_push(S, local_stack, sp, make_uint2(0u, 0x80000000u));
+                        tlas_sp = sp; mesh_id = PTB_FLAT_MESH; identity = true;
+                        cur = make_uint2(unsigned(P.flat_root), 0x80000000u);
+                    } else {
+                        cur = make_uint2(0u, 0x80000000u);
+                        tlas_sp = PTB_INVALID;
+                    }
                     if (STATS) st_rays++;
                 } else exhausted = true;
             }
@@ -169,8 +277,8 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                     unsigned rel = __popc(hits_imask & ~(0xffffffffu << slot));
                     unsigned ni = child_base + rel;
                     float4 n0, n1, n2, n3, n4;
-                    if (ni < unsigned(S.staged)) {
-                        const float4* n = S.tlas + 5 * ni;
+                    if (ni - S.stage_base < unsigned(S.staged)) {
+                        const float4* n = S.tlas + 5 * (ni - S.stage_base);
                         n0 = n[0]; n1 = n[1]; n2 = n[2]; n3 = n[3]; n4 = n[4];
                     } else {
                         const float4* n = P.nodes8 + 5 * size_t(ni);
@@ -193,21 +301,24 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
             if (live && tri.y != 0 && tlas_sp == PTB_INVALID) {
                 unsigned off = msb(tri.y);
                 tri.y &= ~(1u << off);
-                mesh_id = int(tri.x + off);
+                int inst = int(tri.x + off);
+                unsigned root = unsigned(__ldg(P.mesh_roots + inst));
                 if (tri.y != 0) stack_push(S, local_stack, sp, tri);
-                if (cur.y & 0xff000000u) stack_push(S, local_stack, sp, cur);
-                tlas_sp = sp;
-                unsigned root = unsigned(__ldg(P.mesh_roots + mesh_id));
-                identity = (root >> 31) != 0;
-                if (!identity) {
-                    Mat3x4 inv = load_mat(P.mesh_transforms_inv, mesh_id);
-                    ray.o = xform_pos(inv, ray.o);
-                    ray.d = xform_dir(inv, ray.d);
-                    oct4 = ray_octant_inv4(ray.d);
-                    if (STATS) st_xf++;
-                }
-                cur = make_uint2(root & 0x7fffffffu, 0x80000000u);
                 tri.y = 0;
+                if (!(root & PTB_ROOT_MERGED)) {            // merged instances were already intersected through the merged BVH
+                    mesh_id = inst;
+                    if (cur.y & 0xff000000u) stack_push(S, local_stack, sp, cur);
+                    tlas_sp = sp;
+                    identity = (root & PTB_ROOT_IDENTITY) != 0;
+                    if (!identity) {
+                        Mat3x4 inv = load_mat(P.mesh_transforms_inv, mesh_id);
+                        ray.o = xform_pos(inv, ray.o);
+                        ray.d = xform_dir(inv, ray.d);
+                        oct4 = ray_octant_inv4(ray.d);
+                        if (STATS) st_xf++;
+                    }
+                    cur = make_uint2(root & 0x3fffffffu, 0x80000000u);
+                }
             }
             // BLAS level: test triangles, or postpone when too few lanes want to (BVH8.h:233-246)
             bool terminated = false;
@@ -224,7 +335,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                     tri.y &= ~(1u << ti);
                     if (STATS) st_tris++;
                     if (SHADOW) {
-                        if (occludes_triangle(P, int(tri.x + ti), ray, hit.t)) { terminated = true; tri.y = 0; }
+                        if (occludes_triangle(P, mesh_id, int(tri.x + ti), ray, hit.t)) { terminated = true; tri.y = 0; }
                     } else {
                         intersect_triangle(P, mesh_id, int(tri.x + ti), ray, hit);
                     }
@@ -245,6 +356,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                             if (bounce == 0) aov_set(P, PTB_AOV_RADIANCE_DIRECT, px, v);
                             else             aov_add(P, PTB_AOV_RADIANCE_INDIRECT, px, v);
                         } else {
+                            if (hit.mesh_id < -1) hit.mesh_id = __ldg(P.flat_slot_instance + (-(hit.mesh_id) - 2));   // merged slot -> instance
                             q.hit[ray_index] = pack_hit(hit);
                         }
                         live = false; cur = make_uint2(0, 0);
@@ -326,7 +438,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                     stack[sp++] = int(root & 0x7fffffffu);
                 } else {
                     for (int t = first; t < first + int(n); t++) {
-                        if (SHADOW) { if (occludes_triangle(P, t, ray, hit.t)) { occluded = true; break; } }
+                        if (SHADOW) { if (occludes_triangle(P, mesh_id, t, ray, hit.t)) { occluded = true; break; } }
                         else intersect_triangle(P, mesh_id, t, ray, hit);
                     }
                 }
@@ -1073,6 +1185,7 @@ __global__ void k_exchange_wait(const __grid_constant__ Frame P) {
 __global__ void k_begin_pass(const __grid_constant__ Frame P) {
     int* c = reinterpret_cast<int*>(P.counters);
     for (int i = threadIdx.x; i < int(sizeof(Counters) / sizeof(int)); i += blockDim.x) c[i] = 0;
+    if (P.bin_counts) for (int i = threadIdx.x; i < PTB_ORDER_MAX_BOUNCE * 2 * PTB_ORDER_MAX_BINS; i += blockDim.x) P.bin_counts[i] = 0;
     __syncthreads();
     if (threadIdx.x == 0) P.counters->trace[0] = P.local_pixels * P.wave_samples;
 }

@@ -175,4 +175,24 @@ struct Frame {
 
     SVGFBuffers svgf;
     Exchange xchg;
+
+    // Static merge (ptb_api.cu: rebuild_static_merge): every identity-transform instance is also reachable through ONE merged
+    // CWBVH (nodes appended to nodes8 at flat_root); rays walk that first and skip those instances in the TLAS.
+    int           flat_root;          // node index of the merged BVH's root, -1 = none
+    int           flat_all;           // every instance is merged: the TLAS is not traversed at all
+    int           flat_node_count;
+    const float4* flat_tris;          // 3 float4 per merged triangle: p0, e1, e2 (36 B) + original triangle id + merged slot
+    const int*    flat_slot_instance; // merged slot -> current instance index (TLAS leaf order can change between frames)
+
+    // Ray ordering (see k_bin_count / k_bin_scatter): incoherent queues are traced in direction-bin order through `order`
+    int            order_bins;        // 0 = trace in queue order, else 8 (octants) or 64 (8x8 octahedral cells)
+    unsigned*      order;             // position -> ray index, one per queue slot
+    unsigned*      bin_rank;          // ray index -> rank inside its bin
+    unsigned char* bin_key;           // ray index -> bin
+    int*           bin_counts;        // [PTB_ORDER_MAX_BOUNCE][2][64] histogram rows, zeroed by k_begin_pass
 };
+#define PTB_ROOT_IDENTITY 0x80000000u   // mesh_roots bit 31: identity transform (Integrator.cpp, root | identity << 31)
+#define PTB_ROOT_MERGED   0x40000000u   // mesh_roots bit 30 (device copy only): instance lives in the merged static BVH
+#define PTB_FLAT_MESH     (-2147483647 - 1) // mesh_id while traversing the merged BVH; a hit found there carries -(2 + merged slot)
+#define PTB_ORDER_MAX_BINS 64
+#define PTB_ORDER_MAX_BOUNCE 16

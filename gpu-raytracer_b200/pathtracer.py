@@ -68,7 +68,7 @@ class PtbTraversalStats(ctypes.Structure):
 
 
 # every symbol include/ptb.h declares (tests check the built library exports exactly these)
-ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_reserve_wave", "ptb_render_frame",
+ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_reserve_wave", "ptb_set_ray_ordering", "ptb_set_static_merge", "ptb_render_frame",
                "ptb_measure_traversal", "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_download", "ptb_get_ray_stats", "ptb_get_stream", "ptb_export_rows",
                "ptb_assemble_rows", "ptb_exchange_create", "ptb_exchange_connect", "ptb_exchange_connect_ipc", "ptb_exchange_frame", "ptb_exchange_disconnect", "ptb_debug_read", "ptb_launch_count", "ptb_set_timing", "ptb_get_stage_ms", "ptb_stage_name",
                "ptb_error_string"]
@@ -92,6 +92,8 @@ def lib():
         l.ptb_render.argtypes = [vp, ci]
         l.ptb_render_frame.argtypes = [vp, ci, ci]
         l.ptb_reserve_wave.argtypes = [vp, ci]
+        l.ptb_set_ray_ordering.argtypes = [vp, ci]
+        l.ptb_set_static_merge.argtypes = [vp, ci]
         l.ptb_measure_traversal.argtypes = [vp, ci, ctypes.POINTER(PtbTraversalStats)]
         l.ptb_sync.argtypes = [vp]
         l.ptb_get_aov.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(ci)]
@@ -305,6 +307,14 @@ class Pathtracer:
         _check(lib().ptb_assemble_rows(self._ctx, ctypes.c_void_p(device_src), int(max_rows), ctypes.c_void_p(device_dst)), "ptb_assemble_rows")
 
     # ---- frame exchange over peer memory (include/ptb.h: ptb_exchange_*)
+    def set_ray_ordering(self, bins):
+        """0 = trace queues in emission order, 8 / 64 = direction-binned (include/ptb.h: ptb_set_ray_ordering)."""
+        _check(lib().ptb_set_ray_ordering(self._ctx, int(bins)), "ptb_set_ray_ordering")
+
+    def set_static_merge(self, enabled):
+        """include/ptb.h: ptb_set_static_merge (identity-transform instances traced through one merged CWBVH)."""
+        _check(lib().ptb_set_static_merge(self._ctx, int(bool(enabled))), "ptb_set_static_merge")
+
     def exchange_create(self):
         """Allocates this rank's exchange block; returns (device base pointer, 64-byte CUDA IPC handle)."""
         base = ctypes.c_void_p()
@@ -388,9 +398,12 @@ class Pathtracer:
         _check(lib().ptb_set_timing(self._ctx, int(on)), "ptb_set_timing")
 
     def stage_ms(self):
-        ms = (ctypes.c_float * 6)()
-        _check(lib().ptb_get_stage_ms(self._ctx, ms, 6), "ptb_get_stage_ms")
-        return {lib().ptb_stage_name(i).decode(): float(ms[i]) for i in range(6)}
+        n = 0
+        while lib().ptb_stage_name(n):
+            n += 1
+        ms = (ctypes.c_float * n)()
+        _check(lib().ptb_get_stage_ms(self._ctx, ms, n), "ptb_get_stage_ms")
+        return {lib().ptb_stage_name(i).decode(): float(ms[i]) for i in range(n)}
 
     def close(self):
         if getattr(self, "_ctx", None) and self._ctx.value:

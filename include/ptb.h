@@ -165,6 +165,14 @@ int  ptb_export_rows(ptb_ctx* ctx, int aov_type, void* device_dst, int* owned_ro
 /* Inverse of ptb_export_rows for `world` packed tiles laid out rank-major in device_src (each max_rows x pitch float4):
  * scatters them into the full-frame image device_dst (pitch x height float4).  Used after the NCCL all-gather. */
 int  ptb_assemble_rows(ptb_ctx* ctx, const void* device_src, int max_rows, void* device_dst);
+/* Static merge (default on): instances with an identity transform (root bit 31) are additionally built into ONE CWBVH at
+ * upload (CPU SAH build inside ptb_upload_scene / ptb_update_instances) and traced through it instead of TLAS -> BLAS
+ * (BVH8.h:204-232); hits still report the original (mesh_id, triangle_id).  0 = trace the reference's two-level hierarchy only. */
+int  ptb_set_static_merge(ptb_ctx* ctx, int enabled);
+/* Trace order of secondary and shadow rays: 0 = queue (emission) order like the reference's kernel_trace_* (Pathtracer.cu:165-197),
+ * 8 / 64 = counting-sorted by direction bin (octants / 8x8 octahedral cells) before each trace launch.  A scheduling choice
+ * only: every pixel gets the same rays and the same result, bit for bit. */
+int  ptb_set_ray_ordering(ptb_ctx* ctx, int bins);
 /* Frame exchange over NVLink peer memory -- the multi-GPU gather fused into the accumulate kernel (north_star: "a final gather
  * of the tile framebuffers").  The reference is single-GPU (Pathtracer.cpp:738-855 ends in kernel_accumulate writing the one
  * GL surface, Pathtracer.cu:775-796); here the last accumulate of ptb_render_frame stores every finished pixel straight into

@@ -208,3 +208,66 @@ def test_peer_memory_exchange_between_processes():
                         "--master-port", "29533", worker], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("EXCHANGE-OK") == 2, r.stdout[-2000:]
+
+
+def _hits_and_image(blob, cfg, merge):
+    one = pt.Pathtracer(blob, config=pt.default_config(num_bounces=1)); one.set_static_merge(merge)
+    one.render_frames(1); hits = one.primary_hits(); one.close()
+    p = pt.Pathtracer(blob, config=cfg); p.set_static_merge(merge)
+    p.render_frames(2)
+    out = hits, p.get_aov(0), p.ray_stats()
+    p.close()
+    return out
+
+
+def test_static_merge_is_invisible(big):
+    """ptb_set_static_merge: tracing the identity-transform instances through ONE merged CWBVH (default) gives the same
+    primary-hit table (mesh_id, triangle_id, t, uv) and the same image as the reference's TLAS -> BLAS walk, bit for bit --
+    on the full-size scene and on a mixed scene with rotated / scaled instances, all four BSDFs and NEE."""
+    cfg = pt.default_config(num_bounces=4)
+    mixed = scene.build_blob(scene.procedural_scene("soup", seed=11, width=320, height=200, detail=0.6, all_materials=True), 8, rng="fallback")
+    for blob, w in ((big, 1920), (mixed, 320)):
+        ha, ia, sa = _hits_and_image(blob, cfg, True)
+        hb, ib, sb = _hits_and_image(blob, cfg, False)
+        hit = ha[..., 1] != 0xFFFFFFFF
+        assert hit.any() and np.array_equal(ha[..., 1], hb[..., 1])
+        assert np.array_equal(ha[hit], hb[hit])
+        assert np.array_equal(ia[:, :w].view(np.uint32), ib[:, :w].view(np.uint32))
+        assert np.array_equal(sa["trace"], sb["trace"]) and np.array_equal(sa["shadow"], sb["shadow"])
+
+
+def test_static_merge_follows_instance_updates():
+    """ptb_update_instances re-sending the same tables (per-frame fast path) and with an identity instance turning into a
+    moving one (the merged BVH is rebuilt without it): the image stays equal to the un-merged one."""
+    import ctypes
+    d = scene.procedural_scene("soup", seed=4, width=256, height=160, detail=0.5)
+    blob = scene.build_blob(d, 8, rng="fallback")
+    cfg = pt.default_config(num_bounces=3)
+    M = len(blob["mesh_material_ids"])
+    ident = [i for i in range(M) if int(np.asarray(blob["mesh_bvh_root_indices"]).view(np.uint32)[i]) >> 31]
+    assert len(ident) >= 2
+
+    def permuted(blob, move=None):
+        xf = np.array(blob["mesh_transforms"]).copy(); xi = np.array(blob["mesh_transforms_inv"]).copy()
+        roots = np.array(blob["mesh_bvh_root_indices"]).copy()
+        if move is not None:
+            xf[move, 3] += 0.37; xi[move, 3] -= 0.37
+            roots[move] = roots[move] & 0x7FFFFFFF
+        return roots, xf, xi
+
+    for move in (None, ident[0]):
+        roots, xf, xi = permuted(blob, move)
+        outs = []
+        for merge in (True, False):
+            p = pt.Pathtracer(blob, config=cfg); p.set_static_merge(merge)
+            p.render_frames(1)                                      # something is cached before the update
+            tl = np.ascontiguousarray(np.asarray(blob["bvh_nodes"])[: int(blob["tlas_node_count"]) * 80])
+            mats = np.ascontiguousarray(blob["mesh_material_ids"])
+            pt._check(pt.lib().ptb_update_instances(p._ctx, ctypes.c_void_p(tl.ctypes.data), int(blob["tlas_node_count"]), M,
+                                                    ctypes.c_void_p(roots.ctypes.data), ctypes.c_void_p(mats.ctypes.data),
+                                                    ctypes.c_void_p(xf.ctypes.data), ctypes.c_void_p(xi.ctypes.data), ctypes.c_void_p(xf.ctypes.data)), "update")
+            p.sample_index = 0; p.invalidated_gpu_config = True
+            p.render_frames(2)
+            outs.append(p.get_aov(0))
+            p.close()
+        assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
