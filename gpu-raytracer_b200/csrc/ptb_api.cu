@@ -101,7 +101,6 @@ struct ptb_ctx {
     void* xchg_ipc_opened[PTB_MAX_PEERS] = {};        // mappings opened with cudaIpcOpenMemHandle, closed in ptb_destroy
     unsigned xchg_frames = 0;                         // frames pushed + awaited so far (host mirror of ExchangeControl::epoch)
 };
-#define PTB_XCHG_HEADER 256
 
 // CPU SAH + CWBVH builder (host/bvh_build.cpp, linked into this library): used for the merged static BVH
 extern "C" {
@@ -188,6 +187,24 @@ static int allocate_wave_storage(ptb_ctx* ctx, int samples) {
     return 0;
 }
 
+// CUDA loads kernels lazily, on their first launch, and that load synchronises the device.  A frame that ends in a device-side
+// wait for a peer (k_exchange_wait, k_svgf_wait_*) must never meet such a load while the peer's work is still to be enqueued,
+// so every kernel of the library is loaded when the first context is created.
+template <typename K> static void preload(K kernel) { cudaFuncAttributes a; cudaFuncGetAttributes(&a, kernel); }
+static void preload_kernels() {
+    preload(k_generate); preload(k_begin_pass); preload(k_fold_counters); preload(k_sort); preload(k_accumulate);
+    preload(k_trace8<false, false>); preload(k_trace8<true, false>); preload(k_trace8<false, true>); preload(k_trace8<true, true>);
+    preload(k_trace2<false>); preload(k_trace2<true>);
+    preload(k_shade<BSDFDiffuse>); preload(k_shade<BSDFPlastic>); preload(k_shade<BSDFDielectric>); preload(k_shade<BSDFConductor>);
+    preload(k_bin_count<false>); preload(k_bin_count<true>); preload(k_bin_scatter<false>); preload(k_bin_scatter<true>);
+    preload(k_tap_primary_hits); preload(k_export_rows); preload(k_assemble_rows);
+    preload(k_exchange_wait); preload(k_svgf_wait_consumed); preload(k_svgf_push); preload(k_svgf_wait_arrivals); preload(k_svgf_signal_consumed);
+    preload(k_svgf_reproject); preload(k_svgf_variance); preload(k_svgf_atrous); preload(k_svgf_finalize); preload(k_taa); preload(k_taa_finalize);
+    preload(k_clear_framebuffers);
+    preload(k_integrate_dielectric); preload(k_average_dielectric); preload(k_integrate_conductor); preload(k_average_conductor); preload(k_dump_luts);
+    cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------- lifetime
 extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int rank, int world, int band_rows) {
     if (!out || width <= 0 || height <= 0 || world <= 0 || rank < 0 || rank >= world || band_rows <= 0) return PTB_E_BADARG;
@@ -234,6 +251,7 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     F.config.aov_mask = 1u;          // RADIANCE is always on (Pathtracer.cpp:267-268)
     { int e = allocate_wave_storage(ctx, 1); if (e) { ptb_destroy(ctx); return e; } }
 
+    preload_kernels();
     CK(cudaFuncSetAttribute(k_trace8<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CK(cudaFuncSetAttribute(k_trace8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CK(cudaFuncSetAttribute(k_trace8<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -738,6 +756,16 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
     Frame F = ctx->F;
     F.first_sample = first_sample; F.wave_samples = samples;
     F.xchg.push = push && F.xchg.count > 0 && !F.config.enable_svgf;
+    F.xchg.svgf = F.xchg.count > 0 && F.config.enable_svgf;
+    if (F.xchg.svgf) {      // the filter's noisy inputs are produced straight into this rank's exchange block
+        float4* base = F.xchg.frames[F.rank];
+        F.aov[PTB_AOV_RADIANCE_DIRECT].fb   = base + xchg_svgf_plane_offset(F.fb_stride, 0);
+        F.aov[PTB_AOV_RADIANCE_INDIRECT].fb = base + xchg_svgf_plane_offset(F.fb_stride, 1);
+        F.aov[PTB_AOV_ALBEDO].fb            = base + xchg_svgf_plane_offset(F.fb_stride, 2);
+        F.svgf.gbuf_normal_depth            = base + xchg_svgf_plane_offset(F.fb_stride, 3);
+        F.svgf.gbuf_ids                     = reinterpret_cast<int2*>(base + xchg_svgf_plane_offset(F.fb_stride, 4));
+        F.svgf.gbuf_screen_prev             = reinterpret_cast<float2*>(base + xchg_svgf_plane_offset(F.fb_stride, 5));
+    }
     if (F.config.enable_svgf && samples != 1) return PTB_E_STATE;   // SVGF is temporal: one pass per displayed frame
     cudaStream_t st = ctx->stream;
     const int g1d = grid_for(ctx, 8);
@@ -868,7 +896,7 @@ extern "C" int ptb_exchange_create(ptb_ctx* ctx, void** local_base, void* ipc_ha
     CK(cudaSetDevice(ctx->device));
     if (ctx->F.world > PTB_MAX_PEERS) return PTB_E_BADARG;
     if (!ctx->xchg_block) {
-        size_t bytes = PTB_XCHG_HEADER + 2 * (size_t)ctx->F.fb_stride * sizeof(float4);
+        size_t bytes = PTB_XCHG_HEADER + PTB_XCHG_BLOCK_FLOAT4(ctx->F.fb_stride) * sizeof(float4);   // control | 2 frames | SVGF input planes
         CK(cudaMalloc(&ctx->xchg_block, bytes));
         CK(cudaMemset(ctx->xchg_block, 0, bytes));
     }
@@ -937,7 +965,9 @@ extern "C" int ptb_exchange_disconnect(ptb_ctx* ctx) {
 
 extern "C" int ptb_exchange_frame(ptb_ctx* ctx, void** device_ptr, int* pitch) {
     if (!ctx || !device_ptr) return PTB_E_BADARG;
-    if (ctx->F.xchg.count == 0 || ctx->xchg_frames == 0) return PTB_E_STATE;
+    if (ctx->F.xchg.count == 0) return PTB_E_STATE;
+    if (ctx->F.config.enable_svgf) { *device_ptr = ctx->F.display; if (pitch) *pitch = ctx->F.pitch; return 0; }   // every rank filtered the whole frame
+    if (ctx->xchg_frames == 0) return PTB_E_STATE;
     *device_ptr = static_cast<char*>(ctx->xchg_block) + PTB_XCHG_HEADER + (size_t)((ctx->xchg_frames - 1) & 1u) * ctx->F.fb_stride * sizeof(float4);
     if (pitch) *pitch = ctx->F.pitch;
     return 0;

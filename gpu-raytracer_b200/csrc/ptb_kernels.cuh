@@ -1206,6 +1206,71 @@ __global__ void k_tap_primary_hits(const __grid_constant__ Frame P, uint4* out) 
         out[word_pixel(P, P.q[0].pix[i])] = P.q[0].hit[i];                   // slot 0 of the last wave
 }
 
+// ------------------------------------------------------------------------------------------ SVGF input exchange (world > 1)
+PTB_DI unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+PTB_DI void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+PTB_DI bool spin_until_all(const Frame& P, const unsigned* slots, unsigned target) {
+    unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        bool all = true;
+        for (int r = 0; r < P.xchg.count; r++) all = all && int(ld_acquire_sys(slots + r) - target) >= 0;
+        if (all) return true;
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 4000000000ull) return false;
+        __nanosleep(200);
+    }
+}
+// 1. wait until every peer has consumed (filtered + cleared) the previous frame's inputs in ITS block -- they are single-buffered
+__global__ void k_svgf_wait_consumed(const __grid_constant__ Frame P) {
+    ExchangeControl* mine = P.xchg.control[P.rank];
+    if (!spin_until_all(P, mine->svgf_consumed, mine->svgf_epoch)) mine->status = 1u;
+}
+// 2. store this rank's rows of the six input planes into every peer's block, then publish the frame number
+__global__ void __launch_bounds__(256) k_svgf_push(const __grid_constant__ Frame P) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.local_pixels; i += gridDim.x * blockDim.x) {
+        int x, y; local_to_pixel(P, i, x, y);
+        size_t px = size_t(x) + size_t(y) * P.pitch;
+        const float4* mine = P.xchg.frames[P.rank];
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = mine[xchg_svgf_plane_offset(P.fb_stride, k) + px];
+        float2 ids = reinterpret_cast<const float2*>(mine + xchg_svgf_plane_offset(P.fb_stride, 4))[px];
+        float2 sp  = reinterpret_cast<const float2*>(mine + xchg_svgf_plane_offset(P.fb_stride, 5))[px];
+        for (int r = 0; r < P.xchg.count; r++) {
+            if (r == P.rank) continue;
+            float4* dst = P.xchg.frames[r];
+#pragma unroll
+            for (int k = 0; k < 4; k++) dst[xchg_svgf_plane_offset(P.fb_stride, k) + px] = v[k];
+            reinterpret_cast<float2*>(dst + xchg_svgf_plane_offset(P.fb_stride, 4))[px] = ids;
+            reinterpret_cast<float2*>(dst + xchg_svgf_plane_offset(P.fb_stride, 5))[px] = sp;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ExchangeControl* mine = P.xchg.control[P.rank];
+        unsigned done = atomicAdd(&mine->svgf_blocks_done, 1u);
+        if (done == gridDim.x - 1) {
+            mine->svgf_blocks_done = 0;
+            __threadfence_system();
+            const unsigned frame_no = mine->svgf_epoch + 1u;
+            for (int r = 0; r < P.xchg.count; r++) st_release_sys(&P.xchg.control[r]->svgf_arrivals[P.rank], frame_no);
+        }
+    }
+}
+// 3. wait for every rank's rows, advance the epoch
+__global__ void k_svgf_wait_arrivals(const __grid_constant__ Frame P) {
+    ExchangeControl* mine = P.xchg.control[P.rank];
+    if (!spin_until_all(P, mine->svgf_arrivals, mine->svgf_epoch + 1u)) mine->status = 1u;
+    mine->svgf_epoch += 1u;
+}
+// 4. after the filter chain (which ends by clearing the planes): tell every peer this rank's block may be written again
+__global__ void k_svgf_signal_consumed(const __grid_constant__ Frame P) {
+    ExchangeControl* mine = P.xchg.control[P.rank];
+    __threadfence_system();
+    for (int r = 0; r < P.xchg.count; r++) st_release_sys(&P.xchg.control[r]->svgf_consumed[P.rank], mine->svgf_epoch);
+}
+
 // tile export / assemble for the multi-GPU gather
 __global__ void k_export_rows(const __grid_constant__ Frame P, const float4* src, float4* dst) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.local_pixels; i += gridDim.x * blockDim.x) {

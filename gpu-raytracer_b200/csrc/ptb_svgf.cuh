@@ -318,7 +318,12 @@ __global__ void __launch_bounds__(256) k_clear_framebuffers(const __grid_constan
 
 // launch sequence of the SVGF branch of Pathtracer::render (Pathtracer.cpp:798-837)
 static int launch_svgf(Frame& F, cudaStream_t st, int sample_index, int grid, long long* launches) {
-    if (F.world != 1) { fprintf(stderr, "[ptb] SVGF needs the whole frame on one GPU (stencil reach 63 px); gather the noisy AOVs first\n"); return PTB_E_STATE; }
+    // world > 1: the a-trous stencil reaches 126 px and reprojection reads history anywhere, so every rank filters the WHOLE frame
+    // after the ranks have stored their rows of the noisy inputs into each other's blocks (k_svgf_push, peer memory).
+    if (F.world != 1) {
+        if (!(F.xchg.count > 0 && F.xchg.svgf)) { fprintf(stderr, "[ptb] SVGF with world > 1 needs the frame exchange (ptb_exchange_connect*)\n"); return PTB_E_STATE; }
+        k_svgf_wait_consumed<<<1, 1, 0, st>>>(F); k_svgf_push<<<grid, 256, 0, st>>>(F); k_svgf_wait_arrivals<<<1, 1, 0, st>>>(F); (*launches) += 3;
+    }
     k_svgf_reproject<<<grid, 256, 0, st>>>(F, sample_index); (*launches)++;
     float4* din = F.aov[PTB_AOV_RADIANCE_DIRECT].fb; float4* iin = F.aov[PTB_AOV_RADIANCE_INDIRECT].fb;
     float4* dout = F.aov[PTB_AOV_RADIANCE_DIRECT].acc; float4* iout = F.aov[PTB_AOV_RADIANCE_INDIRECT].acc;
@@ -336,5 +341,6 @@ static int launch_svgf(Frame& F, cudaStream_t st, int sample_index, int grid, lo
         k_taa_finalize<<<grid, 256, 0, st>>>(F); (*launches)++;
     }
     k_clear_framebuffers<<<grid, 256, 0, st>>>(F); (*launches)++;
+    if (F.world != 1) { k_svgf_signal_consumed<<<1, 1, 0, st>>>(F); (*launches)++; }
     return 0;
 }

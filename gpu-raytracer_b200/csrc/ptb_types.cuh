@@ -108,13 +108,26 @@ struct ExchangeControl {
     unsigned blocks_done;             // local: CTAs of k_accumulate that finished storing
     unsigned epoch;                   // local: frames completed
     unsigned status;                  // local: 0 ok, 1 = wait timed out
+    // SVGF input exchange (k_svgf_push): the same protocol on its own counters, plus a "consumed" handshake because the planes
+    // are single-buffered (a rank may only store frame k+1 into a peer once that peer has filtered AND cleared frame k)
+    unsigned svgf_arrivals[PTB_MAX_PEERS];
+    unsigned svgf_consumed[PTB_MAX_PEERS];   // slot s: frames rank s has finished consuming
+    unsigned svgf_blocks_done;
+    unsigned svgf_epoch;
 };
 struct Exchange {
     int     count;                    // ranks taking part (0 = off)
     int     push;                     // this launch is the last accumulate of a frame: store to the peers
     float4* frames[PTB_MAX_PEERS];    // peer-mapped base of rank r's block: frame parity p at frames[r] + p * pitch * height
     ExchangeControl* control[PTB_MAX_PEERS];
+    // SVGF with world > 1: the noisy inputs of the filter (3 float4 AOV framebuffers + 3 g-buffers, 80 B per pixel) live in the
+    // exchange block behind the two frames; every rank stores its rows into every peer, then runs the filter on the whole frame.
+    int     svgf;                     // this pass exchanges the SVGF inputs
 };
+#define PTB_XCHG_HEADER 512
+// plane k of the SVGF inputs inside rank r's block (float4 units from frames[r]); planes 0..3 are float4, 4 and 5 are 8-byte
+__host__ __device__ inline size_t xchg_svgf_plane_offset(int fb_stride, int k) { return size_t(fb_stride) * (2 + (k < 4 ? k : 4)) + (k == 5 ? size_t(fb_stride) / 2 : 0); }
+#define PTB_XCHG_BLOCK_FLOAT4(fb_stride) (size_t(fb_stride) * 7)     // 2 frames + 4 float4 planes + 2 half planes
 
 struct Frame {
     // film + tile ownership (rows are dealt to ranks in interleaved bands)

@@ -185,7 +185,9 @@ int  ptb_set_ray_ordering(ptb_ctx* ctx, int bins);
  *   ptb_exchange_frame        device pointer to the complete frame (pitch x height float4) of the last ptb_render_frame; valid
  *                             until the next-but-one ptb_render_frame (two buffers alternate); read it on the ctx stream or
  *                             order the read before the next ptb_render_frame.
- * Every rank must call ptb_render_frame the same number of times.  A peer that does not deliver within 4 s makes the next
+ * With SVGF enabled and world > 1 the exchange carries the filter's noisy inputs instead (every ptb_render stores this rank's rows
+ * of them into every peer, then every rank filters the whole frame): ptb_exchange_frame then returns the display buffer.
+ * Every rank must call ptb_render_frame / ptb_render the same number of times.  A peer that does not deliver within 4 s makes the next
  * ptb_sync return PTB_E_EXCHANGE instead of hanging the GPU. */
 int  ptb_exchange_create(ptb_ctx* ctx, void** local_base, void* ipc_handle_out);
 int  ptb_exchange_connect(ptb_ctx* ctx, void* const* peer_bases);
