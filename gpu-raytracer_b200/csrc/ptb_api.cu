@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -85,6 +86,11 @@ struct ptb_ctx {
     int frames_since_reset = 0;
     std::string last_error;
     float4* svgf_ping[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };
+    // shadow rays of bounce b and extension rays of bounce b+1 are independent until the next sort: the shadow trace runs on a
+    // side stream so that the tail of one persistent trace kernel is filled by the CTAs of the other (render_wave)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap_enabled = true;
     // static merge: identity-transform instances re-built into ONE CWBVH at upload (rebuild_static_merge)
     bool merge_enabled = true;
     std::vector<unsigned char> host_nodes;            // node array as uploaded by the host (for leaf walks)
@@ -217,6 +223,10 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     ctx->device = device;
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    if (const char* v = getenv("PTB_TRACE_OVERLAP")) ctx->overlap_enabled = atoi(v) != 0;     // A/B switch for tools/, default on
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
@@ -265,6 +275,9 @@ extern "C" void ptb_destroy(ptb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (void*& m : ctx->xchg_ipc_opened) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
     if (ctx->xchg_block) { cudaFree(ctx->xchg_block); ctx->xchg_block = nullptr; }
     if (ctx->merge_nodes) cudaFree(ctx->merge_nodes);
@@ -774,6 +787,12 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
 
     k_begin_pass<<<1, 256, 0, st>>>(F); ctx->launches++;
     { StageTimer t(ctx, ST_GENERATE); k_generate<<<g1d, 256, 0, st>>>(F); ctx->launches++; }
+    // Dependencies inside a bounce: trace -> sort -> shade -> { shadow trace, next bounce's trace }.  The two traces only meet
+    // again at the next sort (both deposit into the framebuffer: shadow first, to keep the reference's summation order), so the
+    // shadow trace runs on a side stream; its CTAs and the next closest-hit trace's CTAs fill each other's ramp-down tails.
+    // Per-stage timing (events on the main stream) and the ordering experiment keep everything on one stream.
+    const bool overlap = ctx->overlap_enabled && nee && !ctx->timing && !ctx->stats_mode && F.order_bins == 0;
+    bool side_pending = false;
     for (int bounce = 0; bounce < F.config.num_bounces; bounce++) {
         const bool ordered = F.order_bins > 0 && ctx->bvh_kind == 8 && bounce < PTB_ORDER_MAX_BOUNCE;
         const unsigned* order_c = ordered && bounce > 0 ? F.order : nullptr;       // primary rays are coherent as generated
@@ -785,6 +804,7 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
                                     else                 k_trace8<false, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order_c); }
           else                    k_trace2<false><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
           ctx->launches++; }
+        if (side_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); side_pending = false; }     // shadow[bounce-1] deposits before sort[bounce]
         { StageTimer t(ctx, ST_SORT); k_sort<<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
         { StageTimer t(ctx, ST_SHADE);
           if (ctx->has_type[0]) { k_shade<BSDFDiffuse><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
@@ -795,12 +815,16 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
           k_bin_count<true><<<g1d, 256, 0, st>>>(F, bounce); k_bin_scatter<true><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches += 2; }
         if (nee) {
             StageTimer t(ctx, ST_SHADOW);
-            if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<true, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order_s);
-                                      else                 k_trace8<true, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order_s); }
-            else                    k_trace2<true><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
+            cudaStream_t ss = st;
+            if (overlap) { CK(cudaEventRecord(ctx->ev_fork, st)); CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0)); ss = ctx->side_stream; }
+            if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<true, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), ss>>>(F, bounce, order_s);
+                                      else                 k_trace8<true, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), ss>>>(F, bounce, order_s); }
+            else                    k_trace2<true><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce);
             ctx->launches++;
+            if (overlap) { CK(cudaEventRecord(ctx->ev_join, ctx->side_stream)); side_pending = true; }
         }
     }
+    if (side_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); side_pending = false; }
     { StageTimer t(ctx, ST_POST);
       if (F.config.enable_svgf) {
           int e = launch_svgf(F, st, first_sample, g1d, &ctx->launches); if (e) return e;

@@ -314,3 +314,19 @@ def test_svgf_taa_sharded_equals_single_gpu():
     for p in ranks:
         p.close()
     whole.close()
+
+
+@pytest.mark.parametrize("bins", [8, 64])
+def test_ray_ordering_is_invisible(bins):
+    """ptb_set_ray_ordering: tracing secondary / shadow rays in direction-bin order is a scheduling choice -- same image, same
+    ray counts, in wave mode and pass by pass."""
+    d = scene.procedural_scene("atrium", seed=12, width=352, height=208, detail=0.5)
+    blob = scene.build_blob(d, 8, rng="fallback")
+    cfg = pt.default_config(num_bounces=4)
+    a = pt.Pathtracer(blob, config=cfg); a.reserve_wave(5); a.render_frame(4); a.sync()
+    for wave in (5, 1):
+        b = pt.Pathtracer(blob, config=cfg); b.reserve_wave(wave); b.set_ray_ordering(bins); b.render_frame(4); b.sync()
+        assert np.array_equal(a.get_aov(0).view(np.uint32), b.get_aov(0).view(np.uint32))
+        assert np.array_equal(a.ray_stats()["trace"], b.ray_stats()["trace"]) and np.array_equal(a.ray_stats()["shadow"], b.ray_stats()["shadow"])
+        b.close()
+    a.close()
