@@ -343,11 +343,23 @@ def main():
     n_trace_launch = n_shadow_launch = BOUNCES * waves
     st_one = p.ray_stats(reset=True)
     closest_bytes, shadow_bytes = algorithmic_bytes(trav)
+    # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+    # capture of this configuration (profiles/r1_trace8_wave9_ncu.csv; bench.py cannot run under ncu itself)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_trace8_wave9_ncu.csv")
+    if os.path.exists(tpath) and args.wave == PASSES_PER_STEP and world == 1:
+        import csv
+        rows = [r for r in csv.DictReader(open(tpath)) if r["kernel"].startswith("k_trace8<0")]
+        if rows:
+            traffic = sum((float(r["dram__bytes_read.sum"]) + float(r["dram__bytes_write.sum"])) * 1e6 for r in rows) / len(rows)
+            traffic_src = "profiles/r1_trace8_wave9_ncu.csv (ncu --set full, mean over the closest-hit launches of one frame)"
+
     # trav is one pass; scale node/triangle work to the 9 passes of a frame by the measured ray ratio of that frame
     scale_c = float(st_one["trace"].sum()) / max(trav["rays"][0], 1)
     ach_gbs = closest_bytes * scale_c / (trace_ms * 1e-3) / 1e9
     roofline = {"kernel": "k_trace8<closest-hit>", "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "traffic": None,
+                "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs, burst copy)", "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": closest_bytes * scale_c / n_trace_launch,
                 "avg_launch_ms": trace_ms / n_trace_launch, "launches_timed": n_trace_launch,
                 "algorithmic_bytes_per_ray": closest_bytes / max(trav["rays"][0], 1),
                 "nodes_per_ray": trav["nodes"][0] / max(trav["rays"][0], 1), "triangles_per_ray": trav["triangles"][0] / max(trav["rays"][0], 1),
@@ -363,24 +375,48 @@ def main():
     import ctypes
     lib = pt.lib()
 
+    # The host<->device traffic of a step is pipelined behind the rendering of the next one (separate copy stream, two pinned host
+    # frames): step k uploads its inputs, renders, and queues the device->host read of ITS frame; the read of step k-1 is awaited
+    # at the end of step k.  Every step still pays its upload and its read-back inside the timed region.
+    copy_stream = torch.cuda.Stream()
+    host_frames = [host_frame, torch.empty_like(host_frame).pin_memory()]
+    dev_stage = [torch.empty((HEIGHT, p.screen_pitch, 4), dtype=torch.float32, device="cuda") for _ in range(2)] if gather_mode != "p2p" else None
+    frame_bytes = host_frame.numel() * 4
+    reads = [None, None]
+    step_no = [0]
+
     def e2e_frame():
+        k = step_no[0] & 1
         lib.ptb_update_instances(p._ctx, ctypes.c_void_p(pinned[0].data_ptr()), int(blob["tlas_node_count"]), int(inst[0].size),
                                  *[ctypes.c_void_p(x.data_ptr()) for x in pinned[1:]])
         p.invalidated_camera = True
         one_frame()
-        with torch.cuda.stream(stream):
-            if gather_mode == "nccl":
-                if rank == 0:
-                    host_frame.copy_(frame, non_blocking=True)
-            elif gather_mode == "p2p" and rank != 0:
-                pass                                    # every rank holds the frame; rank 0 is the one that hands it to the host
-            else:
-                ptr = p.exchange_frame() if gather_mode == "p2p" else p.display_device_ptr()[0]
-                lib_rt.cudaMemcpyAsync(ctypes.c_void_p(host_frame.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(host_frame.numel() * 4), 2, ctypes.c_void_p(p.stream()))
+        if rank == 0:
+            if gather_mode == "p2p":
+                src = p.exchange_frame()                # the two exchange buffers alternate: frame k stays intact while k+1 renders
+            else:                                       # single display / assembled buffer: park the frame in a staging copy first (device to device)
+                src0 = frame.data_ptr() if gather_mode == "nccl" else p.display_device_ptr()[0]
+                lib_rt.cudaMemcpyAsync(ctypes.c_void_p(dev_stage[k].data_ptr()), ctypes.c_void_p(src0), ctypes.c_size_t(frame_bytes), 3, ctypes.c_void_p(p.stream()))
+                src = dev_stage[k].data_ptr()
+            rendered = torch.cuda.Event()
+            rendered.record(stream)
+            copy_stream.wait_event(rendered)
+            lib_rt.cudaMemcpyAsync(ctypes.c_void_p(host_frames[k].data_ptr()), ctypes.c_void_p(src), ctypes.c_size_t(frame_bytes), 2, ctypes.c_void_p(copy_stream.cuda_stream))
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+            reads[k] = done
+            if reads[k ^ 1] is not None:
+                reads[k ^ 1].synchronize()              # the previous step's frame is now in host memory
+        step_no[0] += 1
+
+    def e2e_drain():
+        for ev in reads:
+            if ev is not None:
+                ev.synchronize()
         p.sync()
 
     lib_rt = ctypes.CDLL(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart.so.12")) if os.path.exists(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart.so.12")) else ctypes.CDLL("libcudart.so")
-    e2e_frame()
+    e2e_frame(); e2e_drain()
     p.ray_stats(reset=True)
     barrier()
     t0 = time.perf_counter()
@@ -388,6 +424,7 @@ def main():
         ev0.record()
     for _ in range(args.steps):
         e2e_frame()
+    e2e_drain()
     with torch.cuda.stream(stream):
         ev1.record()
     barrier()
@@ -416,7 +453,7 @@ def main():
             line["cpu_bvh_build"] = cpu_bvh_build(blob)
         print(json.dumps(line), flush=True)
     # teardown order matters: tensors that were used on the ctx stream must die before the stream does
-    del packed, gathered, frame, host_frame, pinned
+    del packed, gathered, frame, host_frame, host_frames, dev_stage, pinned, reads
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -195,7 +195,7 @@ PTB_DI unsigned ray_octant_inv4(float3 d) {
 // conversions per node) or the 2^23 magic number: PRMT builds the bits of (8388608 + byte), one FADD (FMA pipe) removes the bias.
 // Both give the same float bit pattern; PTB_CVT_MAGIC_MASK picks, per use site, which pipe pays (bit 0..5 = xmin,ymin,zmin,xmax,ymax,zmax).
 #ifndef PTB_CVT_MAGIC_MASK
-#define PTB_CVT_MAGIC_MASK 0x00
+#define PTB_CVT_MAGIC_MASK 0x09   // x_min and x_max bytes (16 of 48) through the ALU+FMA route: XU 84 % -> balanced; frame 33.56 -> 32.77 ms (tools/gpu_variants_wave.py)
 #endif
 template <int SITE>
 PTB_DI float byte_to_float(unsigned x, int j) {

@@ -12,13 +12,21 @@ rt = ctypes.CDLL("libcudart.so.12")        # already in the process (torch)
 blob = scene.load_blob(os.path.join(ROOT, "data", "_staged", "sponza.npz"))
 merge = int(os.environ.get("PTB_PROF_MERGE", "1"))
 
+wave = int(os.environ.get("PTB_PROF_WAVE", "1"))
 p = pt.Pathtracer(blob, config=pt.default_config(num_bounces=4)); p.set_static_merge(merge)
-for si in range(3):
-    p.render_pass(si)
-p.sync()
-rt.cudaProfilerStart()
-p.render_pass(3); p.sync()
-rt.cudaProfilerStop()
+if wave > 1:                       # the bench configuration: all 9 passes of a frame in one wave (PTB_TRACE_OVERLAP=0 keeps one stream)
+    p.reserve_wave(wave); p.set_timing(True)     # timing mode = plain launches on one stream, no graph
+    p.render_frame(8); p.sync()
+    rt.cudaProfilerStart()
+    p.render_frame(8); p.sync()
+    rt.cudaProfilerStop()
+else:
+    for si in range(3):
+        p.render_pass(si)
+    p.sync()
+    rt.cudaProfilerStart()
+    p.render_pass(3); p.sync()
+    rt.cudaProfilerStop()
 p.close()
 
 if os.environ.get("PTB_PROF_SVGF", "1") == "1":
