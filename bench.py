@@ -385,12 +385,17 @@ def main():
     reads = [None, None]
     step_no = [0]
 
+    host_trace = [] if os.environ.get("PTB_BENCH_TRACE") else None
+
     def e2e_frame():
         k = step_no[0] & 1
+        t_a = time.perf_counter()
         lib.ptb_update_instances(p._ctx, ctypes.c_void_p(pinned[0].data_ptr()), int(blob["tlas_node_count"]), int(inst[0].size),
                                  *[ctypes.c_void_p(x.data_ptr()) for x in pinned[1:]])
         p.invalidated_camera = True
+        t_b = time.perf_counter()
         one_frame()
+        t_c = time.perf_counter()
         if rank == 0:
             if gather_mode == "p2p":
                 src = p.exchange_frame()                # the two exchange buffers alternate: frame k stays intact while k+1 renders
@@ -405,8 +410,11 @@ def main():
             done = torch.cuda.Event()
             done.record(copy_stream)
             reads[k] = done
+            t_d = time.perf_counter()
             if reads[k ^ 1] is not None:
                 reads[k ^ 1].synchronize()              # the previous step's frame is now in host memory
+            if host_trace is not None:
+                host_trace.append((t_b - t_a, t_c - t_b, t_d - t_c, time.perf_counter() - t_d))
         step_no[0] += 1
 
     def e2e_drain():
@@ -429,6 +437,10 @@ def main():
         ev1.record()
     barrier()
     wall_e2e = (time.perf_counter() - t0) * 1e3
+    if host_trace:
+        print("[bench] host ms per e2e step (update_instances, render_frame, queue read-back, wait previous read-back):", file=sys.stderr)
+        for h in host_trace[-args.steps:]:
+            print("   " + " ".join(f"{x * 1e3:7.3f}" for x in h), file=sys.stderr)
     ms_e2e = max(ev0.elapsed_time(ev1), 0.0)
     st2 = p.ray_stats(reset=True)
     t = torch.tensor([max(ms_e2e, wall_e2e)], dtype=torch.float64, device="cuda"); r2 = torch.tensor([float(st2["trace"].sum() + st2["shadow"].sum())], dtype=torch.float64, device="cuda")

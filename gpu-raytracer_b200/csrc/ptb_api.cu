@@ -102,6 +102,14 @@ struct ptb_ctx {
     float4* merge_tris = nullptr;
     int*    merge_slot_instance_dev = nullptr;
     const float4* uploaded_nodes = nullptr;           // device copy of the host's array (kept: the fallback when nothing is merged)
+    // pinned staging for the per-frame uploads (ptb_update_instances): the host arrays are copied here during the call and the
+    // H2D copies run asynchronously behind the previous frame -- the call never waits for the GPU (two arenas alternate)
+    unsigned char* stage_mem[2] = { nullptr, nullptr };
+    unsigned char* stage_dev[2] = { nullptr, nullptr };
+    int stage_segments = 0;
+    size_t stage_cap[2] = { 0, 0 };
+    cudaEvent_t stage_done[2] = { nullptr, nullptr };
+    int stage_cur = 0; size_t stage_used = 0; bool stage_open = false;
     // frame exchange over peer memory
     void* xchg_block = nullptr;                       // {ExchangeControl (256 B), frame[2]} owned by this ctx
     void* xchg_ipc_opened[PTB_MAX_PEERS] = {};        // mappings opened with cudaIpcOpenMemHandle, closed in ptb_destroy
@@ -193,6 +201,23 @@ static int allocate_wave_storage(ptb_ctx* ctx, int samples) {
     return 0;
 }
 
+// One pinned arena = [segment table | payloads].  stage_upload() only appends; staging_flush() ships the arena with ONE H2D copy
+// and ONE small kernel that applies the segments in order (k_apply_uploads) -- nine separate small copies cost ~0.3 ms of
+// serialised copy-engine latency per frame, measured in bench.py's end-to-end loop.
+struct UploadSegment { unsigned long long dst; unsigned offset, words; };
+#define PTB_STAGE_MAX_SEGMENTS 32
+#define PTB_STAGE_TABLE_BYTES (16 + PTB_STAGE_MAX_SEGMENTS * sizeof(UploadSegment))
+__global__ void __launch_bounds__(1024) k_apply_uploads(const unsigned char* arena) {
+    const int n = *reinterpret_cast<const int*>(arena);
+    const UploadSegment* seg = reinterpret_cast<const UploadSegment*>(arena + 16);
+    for (int s = 0; s < n; s++) {                  // in order: later segments may overwrite earlier ones (raw TLAS, then the pruned copy)
+        unsigned* dst = reinterpret_cast<unsigned*>(seg[s].dst);
+        const unsigned* src = reinterpret_cast<const unsigned*>(arena + seg[s].offset);
+        for (unsigned i = threadIdx.x; i < seg[s].words; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+}
+
 // CUDA loads kernels lazily, on their first launch, and that load synchronises the device.  A frame that ends in a device-side
 // wait for a peer (k_exchange_wait, k_svgf_wait_*) must never meet such a load while the peer's work is still to be enqueued,
 // so every kernel of the library is loaded when the first context is created.
@@ -206,7 +231,7 @@ static void preload_kernels() {
     preload(k_tap_primary_hits); preload(k_export_rows); preload(k_assemble_rows);
     preload(k_exchange_wait); preload(k_svgf_wait_consumed); preload(k_svgf_push); preload(k_svgf_wait_arrivals); preload(k_svgf_signal_consumed);
     preload(k_svgf_reproject); preload(k_svgf_variance); preload(k_svgf_atrous); preload(k_svgf_finalize); preload(k_taa); preload(k_taa_finalize);
-    preload(k_clear_framebuffers);
+    preload(k_clear_framebuffers); preload(k_apply_uploads);
     preload(k_integrate_dielectric); preload(k_average_dielectric); preload(k_integrate_conductor); preload(k_average_conductor); preload(k_dump_luts);
     cudaGetLastError();
 }
@@ -280,6 +305,7 @@ extern "C" void ptb_destroy(ptb_ctx* ctx) {
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (void*& m : ctx->xchg_ipc_opened) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
     if (ctx->xchg_block) { cudaFree(ctx->xchg_block); ctx->xchg_block = nullptr; }
+    for (int c = 0; c < 2; c++) { if (ctx->stage_mem[c]) cudaFreeHost(ctx->stage_mem[c]); if (ctx->stage_dev[c]) cudaFree(ctx->stage_dev[c]); if (ctx->stage_done[c]) cudaEventDestroy(ctx->stage_done[c]); }
     if (ctx->merge_nodes) cudaFree(ctx->merge_nodes);
     if (ctx->merge_tris) cudaFree(ctx->merge_tris);
     if (ctx->merge_slot_instance_dev) cudaFree(ctx->merge_slot_instance_dev);
@@ -489,11 +515,66 @@ static void collect_blas_triangles(const unsigned char* nodes, unsigned root, st
     }
 }
 
+static int staging_begin(ptb_ctx* ctx, size_t need) {
+    need += PTB_STAGE_TABLE_BYTES;
+    ctx->stage_cur ^= 1;
+    const int c = ctx->stage_cur;
+    if (ctx->stage_done[c]) CK(cudaEventSynchronize(ctx->stage_done[c]));      // the copy that last read this arena (two calls ago) is long done
+    else CK(cudaEventCreateWithFlags(&ctx->stage_done[c], cudaEventDisableTiming));
+    if (ctx->stage_cap[c] < need) {
+        if (ctx->stage_mem[c]) cudaFreeHost(ctx->stage_mem[c]);
+        if (ctx->stage_dev[c]) cudaFree(ctx->stage_dev[c]);
+        ctx->stage_mem[c] = nullptr; ctx->stage_dev[c] = nullptr; ctx->stage_cap[c] = 0;
+        CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->stage_mem[c]), need));
+        CK(cudaMalloc(reinterpret_cast<void**>(&ctx->stage_dev[c]), need));
+        ctx->stage_cap[c] = need;
+    }
+    ctx->stage_used = PTB_STAGE_TABLE_BYTES; ctx->stage_segments = 0; ctx->stage_open = true;
+    return 0;
+}
+// ship what has been appended so far (one H2D copy + one kernel); the arena stays open for more segments
+static int staging_flush(ptb_ctx* ctx) {
+    const int c = ctx->stage_cur;
+    if (!ctx->stage_open || ctx->stage_segments == 0) return 0;
+    *reinterpret_cast<int*>(ctx->stage_mem[c]) = ctx->stage_segments;
+    // a flush in the middle of a call must not overwrite arena bytes that an earlier, still running flush reads: the device
+    // mirror is only re-used from offset 0 because flushes of one arena are stream-ordered
+    CK(cudaMemcpyAsync(ctx->stage_dev[c], ctx->stage_mem[c], ctx->stage_used, cudaMemcpyHostToDevice, ctx->stream));
+    k_apply_uploads<<<1, 1024, 0, ctx->stream>>>(ctx->stage_dev[c]); ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->stage_done[c], ctx->stream));
+    ctx->stage_segments = 0;
+    return 0;
+}
+// host -> device copy whose source may be changed by the caller as soon as we return
+static int stage_upload(ptb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return 0;
+    const int c = ctx->stage_cur;
+    const size_t padded = (bytes + 15) & ~size_t(15);
+    if (!ctx->stage_open || (bytes & 3) || (reinterpret_cast<size_t>(dst) & 3) || ctx->stage_segments == PTB_STAGE_MAX_SEGMENTS ||
+        ctx->stage_used + padded > ctx->stage_cap[c]) {                             // no arena / odd size / full: plain synchronous copy, in order
+        int fe = staging_flush(ctx); if (fe) return fe;
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    unsigned char* at = ctx->stage_mem[c] + ctx->stage_used;
+    memcpy(at, src, bytes);
+    UploadSegment* seg = reinterpret_cast<UploadSegment*>(ctx->stage_mem[c] + 16) + ctx->stage_segments++;
+    seg->dst = reinterpret_cast<unsigned long long>(dst); seg->offset = (unsigned)ctx->stage_used; seg->words = (unsigned)(bytes / 4);
+    ctx->stage_used += padded;
+    return 0;
+}
+static int staging_end(ptb_ctx* ctx) {
+    int fe = staging_flush(ctx);
+    ctx->stage_open = false;
+    return fe;
+}
+
 static void upload_roots(ptb_ctx* ctx, std::vector<int>& device_roots) {
-    cudaMemcpyAsync((void*)ctx->F.mesh_roots, device_roots.data(), sizeof(int) * device_roots.size(), cudaMemcpyHostToDevice, ctx->stream);
+    stage_upload(ctx, (void*)ctx->F.mesh_roots, device_roots.data(), sizeof(int) * device_roots.size());
     if (ctx->merge_slot_instance_dev && !ctx->merge_slot_instance.empty())
-        cudaMemcpyAsync(ctx->merge_slot_instance_dev, ctx->merge_slot_instance.data(), sizeof(int) * ctx->merge_slot_instance.size(), cudaMemcpyHostToDevice, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);     // both sources are host vectors that may change next call
+        stage_upload(ctx, ctx->merge_slot_instance_dev, ctx->merge_slot_instance.data(), sizeof(int) * ctx->merge_slot_instance.size());
 }
 
 // The host's TLAS still lists the merged instances.  In OUR copy of it (the one rays walk) every leaf slot whose instances are
@@ -529,14 +610,13 @@ static int upload_pruned_tlas(ptb_ctx* ctx) {
     bool all = prune_tlas_node(tl.data(), 0, merged);
     int flat_all = all ? 1 : 0;
     if (flat_all != F.flat_all) { drop_graphs(ctx); F.flat_all = flat_all; }
-    CK(cudaMemcpyAsync(ctx->merge_nodes, tl.data(), tl.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));   // `tl` is a host temporary
-    return 0;
+    return stage_upload(ctx, ctx->merge_nodes, tl.data(), tl.size());
 }
 
 static int rebuild_static_merge(ptb_ctx* ctx) {
     Frame& F = ctx->F;
     drop_graphs(ctx);
+    { int fe = staging_flush(ctx); if (fe) return fe; }      // staged TLAS nodes must be on the device before they are copied below
     CK(cudaStreamSynchronize(ctx->stream));
     const int M = (int)ctx->host_roots.size();
     std::vector<int> slots;
@@ -608,6 +688,7 @@ static int rebuild_static_merge(ptb_ctx* ctx) {
     CK(cudaMalloc(&ctx->merge_tris, flat.size() * sizeof(float4)));
     CK(cudaMemcpyAsync(ctx->merge_tris, flat.data(), flat.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMalloc(&ctx->merge_slot_instance_dev, sizeof(int) * slots.size()));
+    CK(cudaStreamSynchronize(ctx->stream));       // `bfs` and `flat` are host temporaries
     F.nodes8 = ctx->merge_nodes;
     F.flat_root = base; F.flat_node_count = nm; F.flat_all = (int)slots.size() == M ? 1 : 0;
     F.flat_tris = ctx->merge_tris; F.flat_slot_instance = ctx->merge_slot_instance_dev;
@@ -732,21 +813,23 @@ extern "C" int ptb_update_instances(ptb_ctx* ctx, const void* tlas_nodes, int tl
     Frame& F = ctx->F;
     size_t node_bytes = ctx->bvh_kind == 8 ? 80 : 32;
     void* dst = ctx->bvh_kind == 8 ? (void*)F.nodes8 : (void*)F.nodes2;
-    CK(cudaMemcpyAsync(dst, tlas_nodes, node_bytes * tlas_node_count, cudaMemcpyHostToDevice, ctx->stream));
+    { int se = staging_begin(ctx, 3 * node_bytes * (size_t)tlas_node_count + (size_t)mesh_count * 192 + 4096); if (se) return se; }
+    { int se = stage_upload(ctx, dst, tlas_nodes, node_bytes * tlas_node_count); if (se) return se; }
     if (ctx->bvh_kind == 8 && ctx->uploaded_nodes != F.nodes8)      // keep the un-merged copy current as well
-        CK(cudaMemcpyAsync((void*)ctx->uploaded_nodes, tlas_nodes, node_bytes * tlas_node_count, cudaMemcpyHostToDevice, ctx->stream));
+        { int se = stage_upload(ctx, (void*)ctx->uploaded_nodes, tlas_nodes, node_bytes * tlas_node_count); if (se) return se; }
     if (ctx->bvh_kind == 8) {
         F.tlas_nodes = tlas_node_count;
         memcpy(ctx->host_nodes.data(), tlas_nodes, node_bytes * tlas_node_count);
     }
     if (roots) { int re = apply_roots(ctx, roots, mesh_count); if (re) return re; }
     else       { int re = upload_pruned_tlas(ctx); if (re) return re; }
-    if (material_ids) CK(cudaMemcpyAsync((void*)F.mesh_material_ids, material_ids, sizeof(int) * mesh_count, cudaMemcpyHostToDevice, ctx->stream));
-    if (xf) CK(cudaMemcpyAsync((void*)F.mesh_transforms, xf, 48 * (size_t)mesh_count, cudaMemcpyHostToDevice, ctx->stream));
-    if (xf_inv) CK(cudaMemcpyAsync((void*)F.mesh_transforms_inv, xf_inv, 48 * (size_t)mesh_count, cudaMemcpyHostToDevice, ctx->stream));
-    if (xf_prev) CK(cudaMemcpyAsync((void*)F.mesh_transforms_prev, xf_prev, 48 * (size_t)mesh_count, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    int se = 0;
+    if (material_ids) se |= stage_upload(ctx, (void*)F.mesh_material_ids, material_ids, sizeof(int) * mesh_count);
+    if (xf) se |= stage_upload(ctx, (void*)F.mesh_transforms, xf, 48 * (size_t)mesh_count);
+    if (xf_inv) se |= stage_upload(ctx, (void*)F.mesh_transforms_inv, xf_inv, 48 * (size_t)mesh_count);
+    if (xf_prev) se |= stage_upload(ctx, (void*)F.mesh_transforms_prev, xf_prev, 48 * (size_t)mesh_count);
+    if (se) return se;
+    return staging_end(ctx);        // asynchronous: the copies run behind whatever the stream is still rendering
 }
 
 // ---------------------------------------------------------------------------------------------- render
