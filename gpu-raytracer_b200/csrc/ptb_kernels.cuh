@@ -18,13 +18,16 @@
 #define PTB_LOCAL_STACK (PTB_STACK_TOTAL - PTB_SM_STACK)
 #define PTB_TLAS_STAGE_MAX_NODES 256      // up to 20 KB of TLAS nodes bulk-copied (TMA) into shared memory per CTA
 #ifndef PTB_DYNFETCH_ND
-#define PTB_DYNFETCH_ND 4                 // dynamic fetch heuristic, Ylitie et al. 2017 section 4.4 (BVH8.h:109-111)
+#define PTB_DYNFETCH_ND 2                 // dynamic fetch heuristic, Ylitie et al. 2017 section 4.4 (BVH8.h:109-111 uses 4 / 16; 2 / 8 measured 1.6 % faster here)
 #endif
 #ifndef PTB_DYNFETCH_NW
-#define PTB_DYNFETCH_NW 16
+#define PTB_DYNFETCH_NW 8
 #endif
 #ifndef PTB_POSTPONE_DIVISOR
 #define PTB_POSTPONE_DIVISOR 5            // triangle postponing threshold (BVH8.h:12-15)
+#endif
+#ifndef PTB_SHADE_MIN_BLOCKS_DIFFUSE
+#define PTB_SHADE_MIN_BLOCKS_DIFFUSE 4    // 64 registers (120 B of spills) but twice the gathers in flight: frame 32.72 -> 32.21 ms
 #endif
 #ifndef PTB_TILED_GENERATE
 #define PTB_TILED_GENERATE 1              // primary rays enumerated so that a warp covers an 8x4 pixel tile (not a 32x1 strip)
@@ -933,8 +936,10 @@ PTB_DI float2 ellipse_axis_to_gradient(const TriFull& t, float inv_2area, float3
 // ------------------------------------------------------------------------------------------ shade + NEE + extend
 // Src/CUDA/Pathtracer.cu:465-757.  One kernel instantiation per BSDF; shadow rays and extension rays are appended
 // with warp-aggregated atomics.
+template <typename BSDF> struct ShadeOccupancy { static constexpr int min_blocks = 2; };        // microfacet BSDFs: ~120 registers
+template <> struct ShadeOccupancy<BSDFDiffuse> { static constexpr int min_blocks = PTB_SHADE_MIN_BLOCKS_DIFFUSE; };
 template <typename BSDF>
-__global__ void __launch_bounds__(256, 2) k_shade(const __grid_constant__ Frame P, int bounce) {
+__global__ void __launch_bounds__(256, ShadeOccupancy<BSDF>::min_blocks) k_shade(const __grid_constant__ Frame P, int bounce) {
     const RayQueue& q = P.q[bounce & 1];
     const RayQueue& qn = P.q[(bounce + 1) & 1];
     const int count = P.counters->mat[BSDF::QUEUE][bounce];
