@@ -255,15 +255,22 @@ def main():
     if world > 1:
         gather_mode = args.gather
         if gather_mode == "p2p":
-            ok = 1
+            ok, handle, why = 1, b"", ""
             try:
                 _, handle = p.exchange_create()
-                handles = [None] * world
-                dist.all_gather_object(handles, handle)
-                p.exchange_connect_ipc(handles)
-            except Exception as e:                      # e.g. IPC not permitted in this container: say so and use NCCL
-                print(f"[bench] rank {rank}: peer-memory exchange unavailable ({e}); using the NCCL gather", file=sys.stderr, flush=True)
+            except Exception as e:                      # e.g. IPC not permitted in this container
+                ok, why = 0, str(e)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)     # every rank takes part in every collective, whatever happened above
+            if ok and all(len(h) == 64 for h in handles):
+                try:
+                    p.exchange_connect_ipc(handles)
+                except Exception as e:
+                    ok, why = 0, str(e)
+            else:
                 ok = 0
+            if not ok:
+                print(f"[bench] rank {rank}: peer-memory exchange unavailable ({why or 'a peer could not export its block'}); using the NCCL gather", file=sys.stderr, flush=True)
             flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag.item()) == 0:
