@@ -34,7 +34,7 @@ def _run(cmd, cwd=None):
 def build_host(force=False):
     src = os.path.join(PKG_DIR, "host", "bvh_build.cpp")
     out = os.path.join(PKG_DIR, "host", "libptb_host.so")
-    if force or _stale(out, [src]):
+    if force or _stale(out, [src, os.path.join(PKG_DIR, "host", "static_merge.h")]):
         _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", out, src])
     return out
 
@@ -48,7 +48,7 @@ def build_cuda(force=False, verbose=False, defines=(), suffix=""):
     """defines/suffix build tuning variants (libptb<suffix>.so) for A/B measurements; the product is the plain libptb.so."""
     srcs, hdrs = cuda_sources()
     out = os.path.join(PKG_DIR, "csrc", f"libptb{suffix}.so")
-    if force or _stale(out, srcs + hdrs + [os.path.join(PKG_DIR, "host", "bvh_build.cpp")]):
+    if force or _stale(out, srcs + hdrs + [os.path.join(PKG_DIR, "host", "bvh_build.cpp"), os.path.join(PKG_DIR, "host", "static_merge.h")]):
         cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC", "-shared",
                *[f"-D{d}" for d in defines],
                "-Xcompiler", "-ffp-contract=off",

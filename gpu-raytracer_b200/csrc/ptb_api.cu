@@ -14,6 +14,7 @@
 #include "ptb.h"
 #include "ptb_kernels.cuh"
 #include "ptb_post.cuh"
+#include "../host/static_merge.h"
 #include "ptb_svgf.cuh"
 
 #define CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx_fail(ctx, #expr, (int)e__); return (int)e__; } } while (0)
@@ -498,23 +499,6 @@ static int bake_luts(ptb_ctx* ctx) {
 // builder of host/bvh_build.cpp) runs over all of them, the nodes are appended to the node array in breadth-first order and the
 // triangles are stored as compact 48-byte records carrying the original triangle id + merged slot.  Rays walk the merged BVH
 // first and skip merged instances in the TLAS (PTB_ROOT_MERGED); hits report the original (mesh_id, triangle_id).
-static void collect_blas_triangles(const unsigned char* nodes, unsigned root, std::vector<int>& out) {
-    std::vector<unsigned> stack{ root };
-    while (!stack.empty()) {
-        const unsigned char* n = nodes + (size_t)stack.back() * 80; stack.pop_back();
-        unsigned imask = n[15];
-        unsigned base_child, base_tri; memcpy(&base_child, n + 16, 4); memcpy(&base_tri, n + 20, 4);
-        unsigned internal = 0;
-        for (int k = 0; k < 8; k++) {
-            unsigned meta = n[24 + k];
-            if (!meta) continue;
-            if (imask & (1u << k)) { stack.push_back(base_child + internal++); continue; }
-            unsigned count = __builtin_popcount(meta >> 5), first = meta & 31u;
-            for (unsigned t = 0; t < count; t++) out.push_back(int(base_tri + first + t));
-        }
-    }
-}
-
 static int staging_begin(ptb_ctx* ctx, size_t need) {
     need += PTB_STAGE_TABLE_BYTES;
     ctx->stage_cur ^= 1;
@@ -580,34 +564,13 @@ static void upload_roots(ptb_ctx* ctx, std::vector<int>& device_roots) {
 // The host's TLAS still lists the merged instances.  In OUR copy of it (the one rays walk) every leaf slot whose instances are
 // all merged, and every internal child whose whole subtree is, gets meta = 0 -- "empty slot" to the node test, so rays never
 // descend towards instances they already intersected through the merged BVH (imask is left alone: it drives child indexing).
-static bool prune_tlas_node(unsigned char* nodes, unsigned ni, const std::vector<char>& merged) {
-    unsigned char* n = nodes + (size_t)ni * 80;
-    unsigned imask = n[15];
-    unsigned base_child, base_tri; memcpy(&base_child, n + 16, 4); memcpy(&base_tri, n + 20, 4);
-    unsigned internal = 0; bool all = true;
-    for (int k = 0; k < 8; k++) {
-        unsigned meta = n[24 + k];
-        if (imask & (1u << k)) {
-            unsigned child = base_child + internal++;
-            if (!meta) continue;
-            if (prune_tlas_node(nodes, child, merged)) n[24 + k] = 0; else all = false;
-            continue;
-        }
-        if (!meta) continue;
-        unsigned count = __builtin_popcount(meta >> 5), first = meta & 31u;
-        bool leaf_all = true;
-        for (unsigned t = 0; t < count; t++) { unsigned inst = base_tri + first + t; if (inst >= merged.size() || !merged[inst]) leaf_all = false; }
-        if (leaf_all) n[24 + k] = 0; else all = false;
-    }
-    return all;
-}
 static int upload_pruned_tlas(ptb_ctx* ctx) {
     Frame& F = ctx->F;
     if (F.flat_root < 0 || !ctx->merge_nodes || F.tlas_nodes <= 0) return 0;
     std::vector<char> merged(ctx->host_roots.size(), 0);
     for (int i : ctx->merge_slot_instance) if (i >= 0 && (size_t)i < merged.size()) merged[i] = 1;
     std::vector<unsigned char> tl(ctx->host_nodes.begin(), ctx->host_nodes.begin() + (size_t)F.tlas_nodes * 80);
-    bool all = prune_tlas_node(tl.data(), 0, merged);
+    bool all = ptb_merge::prune_tlas(tl.data(), 0, merged);
     int flat_all = all ? 1 : 0;
     if (flat_all != F.flat_all) { drop_graphs(ctx); F.flat_all = flat_all; }
     return stage_upload(ctx, ctx->merge_nodes, tl.data(), tl.size());
@@ -637,7 +600,7 @@ static int rebuild_static_merge(ptb_ctx* ctx) {
     for (size_t k = 0; k < slots.size(); k++) {
         int root = ctx->host_roots[slots[k]];
         tris.clear();
-        collect_blas_triangles(ctx->host_nodes.data(), (unsigned)root & 0x3fffffffu, tris);
+        ptb_merge::collect_leaf_primitives(ctx->host_nodes.data(), (unsigned)root & 0x3fffffffu, tris);
         for (int t : tris) {
             const float4* r = &ctx->host_tri_pos[(size_t)t * 3];
             float3 p0 = make_float3(r[0].x, r[0].y, r[0].z), e1 = make_float3(r[0].w, r[1].x, r[1].y), e2 = make_float3(r[1].z, r[1].w, r[2].x);
@@ -659,21 +622,7 @@ static int rebuild_static_merge(ptb_ctx* ctx) {
     ptbh_free(h);
     // breadth-first re-layout (children of a node stay contiguous and in slot order); child indices become global
     const int base = ctx->node_count;
-    {
-        std::vector<int> queue{ 0 }; queue.reserve(nm);
-        int next = 1;
-        for (size_t qi = 0; qi < queue.size(); qi++) {
-            const unsigned char* src = dfs.data() + (size_t)queue[qi] * 80;
-            unsigned char* dst = bfs.data() + qi * 80;
-            memcpy(dst, src, 80);
-            unsigned old_base; memcpy(&old_base, src + 16, 4);
-            int kids = __builtin_popcount((unsigned)src[15]);
-            unsigned new_base = (unsigned)(base + next);
-            memcpy(dst + 16, &new_base, 4);
-            for (int c = 0; c < kids; c++) queue.push_back((int)old_base + c);
-            next += kids;
-        }
-    }
+    ptb_merge::bfs_relayout(dfs.data(), nm, base, bfs.data());
     std::vector<float4> flat((size_t)n * 3);
     for (int j = 0; j < n; j++) {
         int src = order[j];

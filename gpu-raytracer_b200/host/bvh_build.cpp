@@ -22,6 +22,7 @@
 #include <cstring>
 #include <limits>
 #include <vector>
+#include "static_merge.h"
 
 namespace {
 
@@ -487,5 +488,20 @@ void ptbh_export(void* h, void* nodes_out, int* indices_out, int node_offset, in
 }
 
 void ptbh_free(void* h) { delete static_cast<Built*>(h); }
+
+// C wrappers of host/static_merge.h for the CPU test suite (the product calls the inline functions directly)
+int ptbh_collect_leaf_primitives(const void* nodes, unsigned root, int* out, int capacity) {
+    std::vector<int> v;
+    ptb_merge::collect_leaf_primitives(static_cast<const unsigned char*>(nodes), root, v);
+    for (size_t i = 0; i < v.size() && (int)i < capacity; i++) out[i] = v[i];
+    return (int)v.size();
+}
+int ptbh_prune_tlas(void* nodes, const char* merged, int instance_count) {
+    std::vector<char> m(merged, merged + instance_count);
+    return ptb_merge::prune_tlas(static_cast<unsigned char*>(nodes), 0, m) ? 1 : 0;
+}
+void ptbh_bfs_relayout(const void* dfs, int node_count, int base, void* bfs) {
+    ptb_merge::bfs_relayout(static_cast<const unsigned char*>(dfs), node_count, base, static_cast<unsigned char*>(bfs));
+}
 
 } // extern "C"

@@ -91,3 +91,89 @@ def test_tlas_slots_and_instance_tables():
     for a, b in zip(t, ti):
         A = np.vstack([a, [0, 0, 0, 1]]); B = np.vstack([b, [0, 0, 0, 1]])
         assert np.allclose(A @ B, np.eye(4), atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------- static-merge host helpers
+def _merge_lib():
+    import ctypes
+    lib = scene.hostlib()
+    lib.ptbh_collect_leaf_primitives.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_int]
+    lib.ptbh_prune_tlas.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+    lib.ptbh_bfs_relayout.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    return lib
+
+
+def _collect(lib, nodes, root, cap):
+    out = np.empty(cap, dtype=np.int32)
+    n = lib.ptbh_collect_leaf_primitives(nodes.ctypes.data, int(root), out.ctypes.data, cap)
+    assert n <= cap
+    return out[:n]
+
+
+def test_static_merge_collects_each_instance_triangles():
+    """host/static_merge.h::collect_leaf_primitives walks a BLAS of the uploaded node array and must return exactly the
+    triangle range of that mesh (what rebuild_static_merge feeds to the merged SAH build)."""
+    lib = _merge_lib()
+    blob = scene.build_blob(scene.procedural_scene("soup", seed=5, width=64, height=64, detail=0.5), 8, rng="fallback")
+    nodes = np.ascontiguousarray(blob["bvh_nodes"])
+    roots = np.asarray(blob["mesh_bvh_root_indices"]).view(np.uint32)
+    T = len(blob["triangles"])
+    for i, root in enumerate(roots):
+        got = _collect(lib, nodes, root & 0x3FFFFFFF, T)
+        first, count = int(blob["mesh_tri_first"][i]), int(blob["mesh_tri_count"][i])
+        assert sorted(got.tolist()) == list(range(first, first + count))
+    # the TLAS lists every instance exactly once
+    inst = _collect(lib, nodes, 0, 4 * len(roots))
+    assert sorted(inst.tolist()) == list(range(len(roots)))
+
+
+def test_static_merge_bfs_relayout_preserves_the_tree():
+    """bfs_relayout: same leaves, root first, children contiguous, and the first nodes are the top levels (depth never decreases)."""
+    lib = _merge_lib()
+    rng = np.random.default_rng(3)
+    tris = (rng.random((4000, 3, 3)) * 10.0).astype(np.float32)
+    tris[:, 1:] = tris[:, :1] + (rng.random((4000, 2, 3)).astype(np.float32) - 0.5) * 0.3
+    b = scene.build_blas(tris, 8)
+    dfs, idx = b.export(0, 0)
+    bfs = np.zeros_like(dfs)
+    base = 1000
+    lib.ptbh_bfs_relayout(dfs.ctypes.data, b.node_count, base, bfs.ctypes.data)
+    # walk the relaid tree (indices are global: shift the array so that node `base` is at offset base)
+    padded = np.concatenate([np.zeros(base * 80, dtype=np.uint8), bfs])
+    want = sorted(_collect(lib, dfs, 0, 3 * len(tris)).tolist())
+    got = sorted(_collect(lib, padded, base, 3 * len(tris)).tolist())
+    assert got == want == list(range(len(tris)))
+    # breadth-first: depth of node i is non-decreasing in i
+    n = bfs.reshape(-1, 80)
+    depth = np.zeros(b.node_count, dtype=np.int32)
+    for i in range(b.node_count):
+        kids = bin(int(n[i, 15])).count("1")
+        first = int(n[i, 16:20].view(np.uint32)[0]) - base
+        assert kids == 0 or (i < first and first + kids <= b.node_count)
+        depth[first:first + kids] = depth[i] + 1
+    assert (np.diff(depth) >= 0).all() and depth[0] == 0
+
+
+def test_static_merge_prunes_the_tlas():
+    """prune_tlas blanks every slot that only leads to merged instances: walking the pruned TLAS reaches all un-merged instances,
+    and merged ones only where they share a leaf with an un-merged one; merging everything empties the root."""
+    lib = _merge_lib()
+    rng = np.random.default_rng(1)
+    lo = (rng.random((97, 3)) * 50).astype(np.float32)
+    boxes = np.concatenate([lo, lo + 1.0 + rng.random((97, 3)).astype(np.float32)], axis=1)
+    tl = scene.build_tlas(boxes, 8)
+    nodes, order = tl.export(0, 0)
+    M = len(boxes)
+    merged = (rng.random(M) < 0.8)
+    pruned = nodes.copy()
+    all_gone = lib.ptbh_prune_tlas(pruned.ctypes.data, merged.astype(np.int8).tobytes(), M)
+    assert all_gone == 0
+    reach = set(_collect(lib, pruned, 0, 4 * M).tolist())
+    assert set(np.where(~merged)[0].tolist()) <= reach
+    assert len(reach) < M                                            # something was actually pruned
+    # a merged instance is only still reachable through a leaf it shares with an un-merged one: its leaf group has an un-merged member
+    full = _collect(lib, nodes, 0, 4 * M).tolist()
+    assert sorted(full) == list(range(M))
+    everything = nodes.copy()
+    assert lib.ptbh_prune_tlas(everything.ctypes.data, np.ones(M, dtype=np.int8).tobytes(), M) == 1
+    assert len(_collect(lib, everything, 0, 4 * M)) == 0
