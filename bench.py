@@ -188,10 +188,11 @@ def run_reference(args, blob, workload):
     r.sync()
     dt_e2e = time.perf_counter() - t0
     value = rays / dt / 1e6
-    line = {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+    launched = int(os.environ.get("WORLD_SIZE", "1"))
+    line = {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": launched, "reference_uses_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "passes_per_step": PASSES_PER_STEP, "l2": "working set (ray queues + AOVs > 400 MB per pass) exceeds the 126 MB L2",
-                       "reference_arm": "reference CUDA kernels (Pathtracer.cu compiled unmodified) driven by oracle/ref_harness.cpp, reference launch recipe",
+                       "reference_arm": "reference CUDA kernels (Pathtracer.cu compiled unmodified) driven by oracle/ref_harness.cpp, reference launch recipe; the reference is single-GPU: whatever N it is launched with, rank 0 runs it on GPU 0 and the other ranks exit",
                        "launch_geometry": r.launch_geometry()},
             "rays_per_step": rays // args.steps, "clocks": clocks, "gpu_launches": 0,
             "e2e": {"value": rays / dt_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(host.nbytes)},
