@@ -138,17 +138,19 @@ int  ptb_update_instances(ptb_ctx* ctx, const void* tlas_nodes, int tlas_node_co
                           const float* transforms, const float* transforms_inv, const float* transforms_prev);
 /* Pathtracer::render() for one pass with the given sample_index (Pathtracer.cpp:738-855). Asynchronous on the ctx stream. */
 int  ptb_render(ptb_ctx* ctx, int sample_index);
-/* Number of pass slots a wave can carry (default 1).  With `samples` > 1, ptb_render_frame traces up to that many consecutive
+/* Replaces the reference's batching (BATCH_SIZE = 1080 x 720 pixels, Src/CUDA/Common.h:69-71; a blocking 4-KB upload between batches, Pathtracer.cpp:789-795):
+ * number of pass slots a wave can carry (default 1).  With `samples` > 1, ptb_render_frame traces up to that many consecutive
  * passes TOGETHER (every ray carries its pass slot; each slot has its own framebuffer plane; the accumulate pass folds the
  * planes in pass order, so accumulators are bit-identical to tracing pass by pass).  Re-allocates the ray queues. */
 int  ptb_reserve_wave(ptb_ctx* ctx, int samples);
-/* `num_passes` consecutive ptb_render calls (sample_index = first_sample_index ...) replayed as ONE CUDA graph: the launch
+/* The reference's `-N <samples>` capture loop (Src/Main.cpp:137-142: update + render until sample_index == N):
+ * `num_passes` consecutive ptb_render calls (sample_index = first_sample_index ...) replayed as ONE CUDA graph: the launch
  * sequence of a frame is static (queue sizes live in device memory), so the ~20 launches per pass cost one graph launch per
  * frame.  Graphs are cached per (first_sample_index, num_passes) and dropped whenever camera / config / instances change. */
 int  ptb_render_frame(ptb_ctx* ctx, int first_sample_index, int num_passes);
-/* Same as ptb_render, with the instrumented trace kernels; blocks and returns the pass's traversal statistics. */
+/* Same as ptb_render, with the instrumented trace kernels (the reference has no counterpart; feeds SURVEY 8d's algorithmic bytes); blocks and returns the pass's traversal statistics. */
 int  ptb_measure_traversal(ptb_ctx* ctx, int sample_index, ptb_traversal_stats* out);
-/* cuStreamSynchronize equivalent */
+/* cuStreamSynchronize equivalent (the reference's blocking set_value at the end of Pathtracer::render, Pathtracer.cpp:845-847, plays this role) */
 int  ptb_sync(ptb_ctx* ctx);
 /* get_aov(type).framebuffer / .accumulator (Integrator.h:247): device pointer to pitch x height float4 */
 int  ptb_get_aov(ptb_ctx* ctx, int aov_type, int accumulated, void** device_ptr, int* pitch);
