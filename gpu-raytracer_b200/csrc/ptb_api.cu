@@ -620,6 +620,14 @@ static int rebuild_static_merge(ptb_ctx* ctx) {
     std::vector<int> order((size_t)ptbh_index_count(h));
     ptbh_export(h, dfs.data(), order.data(), 0, 0);
     ptbh_free(h);
+    // the merged tree is deeper than any single BLAS: keep the two-level walk if it could outgrow the traversal stack
+    // (BVH_STACK_SIZE = 32 entries, two per level, plus the TLAS root that waits underneath)
+    if (2 * ptb_merge::max_depth(dfs.data(), 0) + 3 > PTB_STACK_TOTAL) {
+        fprintf(stderr, "[ptb] static merge skipped: merged BVH too deep for the %d-entry traversal stack\n", PTB_STACK_TOTAL);
+        ctx->merge_slot_root.clear(); ctx->merge_slot_instance.clear();
+        upload_roots(ctx, ctx->host_roots);
+        return 0;
+    }
     // breadth-first re-layout (children of a node stay contiguous and in slot order); child indices become global
     const int base = ctx->node_count;
     ptb_merge::bfs_relayout(dfs.data(), nm, base, bfs.data());

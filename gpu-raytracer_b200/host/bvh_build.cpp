@@ -500,6 +500,7 @@ int ptbh_prune_tlas(void* nodes, const char* merged, int instance_count) {
     std::vector<char> m(merged, merged + instance_count);
     return ptb_merge::prune_tlas(static_cast<unsigned char*>(nodes), 0, m) ? 1 : 0;
 }
+int ptbh_max_depth(const void* nodes, unsigned root) { return ptb_merge::max_depth(static_cast<const unsigned char*>(nodes), root); }
 void ptbh_bfs_relayout(const void* dfs, int node_count, int base, void* bfs) {
     ptb_merge::bfs_relayout(static_cast<const unsigned char*>(dfs), node_count, base, static_cast<unsigned char*>(bfs));
 }

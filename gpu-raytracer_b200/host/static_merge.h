@@ -32,6 +32,22 @@ inline void collect_leaf_primitives(const unsigned char* nodes, unsigned root, s
     }
 }
 
+// Longest root-to-leaf path, in nodes.  The traversal keeps at most two stack entries per level (the rest of a node group and a
+// postponed triangle group), so 2 * depth + 2 entries bound its stack.
+inline int max_depth(const unsigned char* nodes, unsigned root) {
+    struct Item { unsigned node; int depth; };
+    std::vector<Item> stack{ { root, 1 } };
+    int deepest = 0;
+    while (!stack.empty()) {
+        Item it = stack.back(); stack.pop_back();
+        if (it.depth > deepest) deepest = it.depth;
+        NodeView v{ nodes + (size_t)it.node * 80 };
+        unsigned internal = 0;
+        for (int k = 0; k < 8; k++) if (v.imask() & (1u << k)) { unsigned child = v.base_child() + internal++; if (v.meta(k)) stack.push_back({ child, it.depth + 1 }); }
+    }
+    return deepest;
+}
+
 // Blank (meta = 0: "empty slot" to the node test) every leaf slot whose instances are all merged and every internal child whose
 // whole subtree is; imask is left alone because it drives child indexing.  Returns true when nothing below `ni` is left.
 inline bool prune_tlas(unsigned char* nodes, unsigned ni, const std::vector<char>& merged) {

@@ -177,3 +177,25 @@ def test_static_merge_prunes_the_tlas():
     everything = nodes.copy()
     assert lib.ptbh_prune_tlas(everything.ctypes.data, np.ones(M, dtype=np.int8).tobytes(), M) == 1
     assert len(_collect(lib, everything, 0, 4 * M)) == 0
+
+
+def test_static_merge_depth_bound():
+    """max_depth (the guard that keeps the merged tree inside the 32-entry traversal stack): a single node is depth 1, the depth
+    of a built tree is what a recursive walk finds, and the real scenes stay far below the bound."""
+    import ctypes
+    lib = _merge_lib()
+    lib.ptbh_max_depth.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+    rng = np.random.default_rng(8)
+    one = (rng.random((2, 3, 3))).astype(np.float32)
+    b1 = scene.build_blas(one, 8); n1, _ = b1.export(0, 0)
+    assert lib.ptbh_max_depth(n1.ctypes.data, 0) == 1
+    tris = (rng.random((20000, 3, 3)) * 20.0).astype(np.float32)
+    tris[:, 1:] = tris[:, :1] + (rng.random((20000, 2, 3)).astype(np.float32) - 0.5) * 0.2
+    b = scene.build_blas(tris, 8); nd, _ = b.export(0, 0)
+    n = nd.reshape(-1, 80)
+
+    def walk(i):
+        kids = bin(int(n[i, 15])).count("1"); base = int(n[i, 16:20].view(np.uint32)[0])
+        return 1 + max([walk(base + k) for k in range(kids)], default=0)
+    d = lib.ptbh_max_depth(nd.ctypes.data, 0)
+    assert d == walk(0) and 3 <= d and 2 * d + 3 <= 32
