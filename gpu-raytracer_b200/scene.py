@@ -747,7 +747,7 @@ def save_blob(blob, path):
             arrays[f"tex{i}_l{l}"] = np.asarray(lv, dtype=np.uint8)
     arrays["meta_json"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-    np.savez(path, **arrays)
+    np.savez_compressed(path, **arrays)      # the staged blobs travel to the GPU box with every gpurun call
 
 
 def load_blob(path):
