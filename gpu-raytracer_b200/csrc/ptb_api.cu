@@ -87,6 +87,7 @@ struct ptb_ctx {
     int frames_since_reset = 0;
     std::string last_error;
     float4* svgf_ping[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };
+    int pixel_query_host[3] = { -1, -1, -1 };
     // shadow rays of bounce b and extension rays of bounce b+1 are independent until the next sort: the shadow trace runs on a
     // side stream so that the tail of one persistent trace kernel is filled by the CTAs of the other (render_wave)
     cudaStream_t side_stream = nullptr;
@@ -282,7 +283,8 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     F.fb_stride = (int)pixels;
     F.pix_bits = 1; while ((1ull << F.pix_bits) < pixels) F.pix_bits++;
     F.wave_samples = 1; F.first_sample = 0;
-    if (dev_alloc(ctx, &F.display, pixels) || dev_alloc(ctx, &ctx->tap_hits, pixels)) { ptb_destroy(ctx); return PTB_E_STATE; }
+    if (dev_alloc(ctx, &F.display, pixels) || dev_alloc(ctx, &ctx->tap_hits, pixels) || dev_alloc(ctx, &F.pixel_query, 4)) { ptb_destroy(ctx); return PTB_E_STATE; }
+    CK(cudaMemsetAsync(F.pixel_query, 0xff, 4 * sizeof(int), ctx->stream));      // {INVALID, INVALID, INVALID}: no query pending
     CK(cudaMemsetAsync(F.display, 0, pixels * sizeof(float4), ctx->stream));
     F.config.aov_mask = 1u;          // RADIANCE is always on (Pathtracer.cpp:267-268)
     { int e = allocate_wave_storage(ctx, 1); if (e) { ptb_destroy(ctx); return e; } }
@@ -1097,6 +1099,25 @@ extern "C" int ptb_download(ptb_ctx* ctx, int aov_type, int accumulated, float* 
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+// set_pixel_query (Integrator.h:266-277) / the read-back in Integrator::update (Integrator.cpp:483-494)
+extern "C" int ptb_set_pixel_query(ptb_ctx* ctx, int x, int y) {
+    if (!ctx || x < 0 || y < 0 || x >= ctx->F.width || y >= ctx->F.height) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    ctx->pixel_query_host[0] = x + y * ctx->F.pitch; ctx->pixel_query_host[1] = -1; ctx->pixel_query_host[2] = -1;
+    CK(cudaMemcpyAsync(ctx->F.pixel_query, ctx->pixel_query_host, 3 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+extern "C" int ptb_get_pixel_query(ptb_ctx* ctx, int* mesh_id, int* triangle_id) {
+    if (!ctx || !mesh_id || !triangle_id) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    int q[3];
+    CK(cudaMemcpyAsync(q, ctx->F.pixel_query, sizeof(q), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *mesh_id = q[1]; *triangle_id = q[2];
+    CK(cudaMemsetAsync(ctx->F.pixel_query, 0xff, 3 * sizeof(int), ctx->stream));  // query consumed: pixel_index back to INVALID
+    return 0;
+}
+
 extern "C" int ptb_get_ray_stats(ptb_ctx* ctx, ptb_ray_stats* out, int reset) {
     if (!ctx || !out) return PTB_E_BADARG;
     CK(cudaSetDevice(ctx->device));

@@ -605,6 +605,9 @@ __global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, i
                 ended = true;
             }
             if (!ended) {
+                if (bounce == 0 && P.pixel_query[0] == pixel_index) {     // GUI picking (Pathtracer.cu:345-348); pixel_index is -1 unless a query is pending
+                    P.pixel_query[1] = hit.mesh_id; P.pixel_query[2] = hit.triangle_id;
+                }
                 int material_id = P.mesh_material_ids[hit.mesh_id];
                 int mtype = P.material_types[material_id];
                 if (mtype == PTB_MAT_LIGHT) {                          // Pathtracer.cu:354-422

@@ -153,6 +153,7 @@ struct Frame {
     TraceStats* trace_stats;
     AOVBuffers  aov[PTB_AOV_COUNT];
     float4*     display;              // what the reference writes to its GL surface
+    int*        pixel_query;          // {pixel_index, mesh_id, triangle_id} (PixelQuery, Pathtracer.cu:120): filled by k_sort at bounce 0
 
     // scene
     const float4*        triangles;   // 6 float4 per triangle

@@ -69,7 +69,7 @@ class PtbTraversalStats(ctypes.Structure):
 
 # every symbol include/ptb.h declares (tests check the built library exports exactly these)
 ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_reserve_wave", "ptb_set_ray_ordering", "ptb_set_static_merge", "ptb_render_frame",
-               "ptb_measure_traversal", "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_download", "ptb_get_ray_stats", "ptb_get_stream", "ptb_export_rows",
+               "ptb_measure_traversal", "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_download", "ptb_get_ray_stats", "ptb_set_pixel_query", "ptb_get_pixel_query", "ptb_get_stream", "ptb_export_rows",
                "ptb_assemble_rows", "ptb_exchange_create", "ptb_exchange_connect", "ptb_exchange_connect_ipc", "ptb_exchange_frame", "ptb_exchange_disconnect", "ptb_debug_read", "ptb_launch_count", "ptb_set_timing", "ptb_get_stage_ms", "ptb_stage_name",
                "ptb_error_string"]
 
@@ -101,6 +101,8 @@ def lib():
         l.ptb_download.argtypes = [vp, ci, ci, vp]
         l.ptb_get_ray_stats.argtypes = [vp, ctypes.POINTER(PtbRayStats), ci]
         l.ptb_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
+        l.ptb_set_pixel_query.argtypes = [vp, ci, ci]
+        l.ptb_get_pixel_query.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
         l.ptb_exchange_create.argtypes = [vp, ctypes.POINTER(vp), vp]
         l.ptb_exchange_connect.argtypes = [vp, ctypes.POINTER(vp)]
         l.ptb_exchange_connect_ipc.argtypes = [vp, vp]
@@ -310,6 +312,16 @@ class Pathtracer:
     def set_ray_ordering(self, bins):
         """0 = trace queues in emission order, 8 / 64 = direction-binned (include/ptb.h: ptb_set_ray_ordering)."""
         _check(lib().ptb_set_ray_ordering(self._ctx, int(bins)), "ptb_set_ray_ordering")
+
+    def set_pixel_query(self, x, y):
+        """Integrator::set_pixel_query (Integrator.h:266-277): the next pass records what the primary ray of pixel (x, y) hits."""
+        _check(lib().ptb_set_pixel_query(self._ctx, int(x), int(y)), "ptb_set_pixel_query")
+
+    def get_pixel_query(self):
+        """(mesh_id, triangle_id) of the pending query, (-1, -1) for sky; clears the query."""
+        m, t = ctypes.c_int(), ctypes.c_int()
+        _check(lib().ptb_get_pixel_query(self._ctx, ctypes.byref(m), ctypes.byref(t)), "ptb_get_pixel_query")
+        return m.value, t.value
 
     def set_static_merge(self, enabled):
         """include/ptb.h: ptb_set_static_merge (identity-transform instances traced through one merged CWBVH)."""

@@ -158,6 +158,11 @@ int  ptb_get_aov(ptb_ctx* ctx, int aov_type, int accumulated, void** device_ptr,
 int  ptb_get_display(ptb_ctx* ctx, void** device_ptr, int* pitch);
 /* Copies an AOV (or the display image when aov_type < 0) to host memory: pitch x height x float4 */
 int  ptb_download(ptb_ctx* ctx, int aov_type, int accumulated, float* host_dst);
+/* set_pixel_query(x, y) (Integrator.h:266-277): the next rendered pass records which (mesh_id, triangle_id) the primary ray of that
+ * pixel hits (kernel_sort, Pathtracer.cu:345-348).  ptb_get_pixel_query blocks, returns them (-1, -1 = sky or nothing rendered yet)
+ * and clears the query like Integrator::update does (Integrator.cpp:483-494); mesh_id is the instance index in TLAS leaf order. */
+int  ptb_set_pixel_query(ptb_ctx* ctx, int x, int y);
+int  ptb_get_pixel_query(ptb_ctx* ctx, int* mesh_id, int* triangle_id);
 /* Ray counters (device buffer_sizes, summed over passes) */
 int  ptb_get_ray_stats(ptb_ctx* ctx, ptb_ray_stats* out, int reset);
 /* CUDA stream the ctx launches on (cudaStream_t as void*), e.g. to enqueue a collective after ptb_render */

@@ -330,3 +330,25 @@ def test_ray_ordering_is_invisible(bins):
         assert np.array_equal(a.ray_stats()["trace"], b.ray_stats()["trace"]) and np.array_equal(a.ray_stats()["shadow"], b.ray_stats()["shadow"])
         b.close()
     a.close()
+
+
+def test_pixel_query_reports_the_primary_hit():
+    """set_pixel_query (Integrator.h:266-277 / Pathtracer.cu:345-348): after the next pass the query holds the (mesh_id,
+    triangle_id) of that pixel's primary hit -- the same ids as the primary-hit table -- and (-1, -1) for a sky pixel; reading
+    it clears the query."""
+    d = scene.procedural_scene("soup", seed=6, width=160, height=96, detail=0.5)
+    blob = scene.build_blob(d, 8, rng="fallback")
+    p = pt.Pathtracer(blob, config=pt.default_config(num_bounces=1))
+    p.render_pass(1); p.sync()
+    hits = p.primary_hits()[:96, :160]
+    hit_px = np.argwhere(hits[..., 1] != 0xFFFFFFFF); sky_px = np.argwhere(hits[..., 1] == 0xFFFFFFFF)
+    assert len(hit_px) and len(sky_px)
+    y, x = (int(v) for v in hit_px[len(hit_px) // 2])
+    p.set_pixel_query(x, y); p.render_pass(1)
+    assert p.get_pixel_query() == (int(hits[y, x, 0]), int(hits[y, x, 1]))
+    p.render_pass(1)
+    assert p.get_pixel_query() == (-1, -1)                     # consumed: nothing pending any more
+    y, x = (int(v) for v in sky_px[0])
+    p.set_pixel_query(x, y); p.render_pass(1)
+    assert p.get_pixel_query() == (-1, -1)
+    p.close()
