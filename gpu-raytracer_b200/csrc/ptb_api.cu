@@ -10,6 +10,7 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "ptb.h"
 #include "ptb_kernels.cuh"
@@ -18,6 +19,8 @@
 #include "ptb_svgf.cuh"
 
 #define CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx_fail(ctx, #expr, (int)e__); return (int)e__; } } while (0)
+// inside ptb_create: a failure must not leak the half-built context
+#define CKC(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx_fail(ctx, #expr, (int)e__); ptb_destroy(ctx); return (int)e__; } } while (0)
 #define CKD(expr) do { CUresult r__ = (expr); if (r__ != CUDA_SUCCESS) { ctx_fail(ctx, #expr, 1000 + (int)r__); return 1000 + (int)r__; } } while (0)
 
 // Driver-API entry points are resolved through the runtime (cudaGetDriverEntryPoint) so libptb.so carries no link-time
@@ -100,6 +103,7 @@ struct ptb_ctx {
     std::vector<int> host_roots;                      // roots as last given by the host
     std::vector<int> merge_slot_root;                 // merged slot -> BLAS root (identity bit included)
     std::vector<int> merge_slot_instance;             // merged slot -> instance index in the current TLAS leaf order
+    std::vector<int> merge_decided_roots;             // sorted roots of the identity instances the last merge decision (built, disabled or skipped) was taken on
     float4* merge_nodes = nullptr;                    // device: [host node array | merged nodes], owned
     float4* merge_tris = nullptr;
     int*    merge_slot_instance_dev = nullptr;
@@ -227,7 +231,7 @@ template <typename K> static void preload(K kernel) { cudaFuncAttributes a; cuda
 static void preload_kernels() {
     preload(k_generate); preload(k_begin_pass); preload(k_fold_counters); preload(k_sort); preload(k_accumulate);
     preload(k_trace8<false, false>); preload(k_trace8<true, false>); preload(k_trace8<false, true>); preload(k_trace8<true, true>);
-    preload(k_trace2<false>); preload(k_trace2<true>);
+    preload(k_trace2<false, false>); preload(k_trace2<true, false>); preload(k_trace2<false, true>); preload(k_trace2<true, true>);
     preload(k_shade<BSDFDiffuse>); preload(k_shade<BSDFPlastic>); preload(k_shade<BSDFDielectric>); preload(k_shade<BSDFConductor>);
     preload(k_bin_count<false>); preload(k_bin_count<true>); preload(k_bin_scatter<false>); preload(k_bin_scatter<true>);
     preload(k_tap_primary_hits); preload(k_export_rows); preload(k_assemble_rows);
@@ -248,14 +252,14 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     ptb_ctx* ctx = new (std::nothrow) ptb_ctx();
     if (!ctx) return PTB_E_STATE;
     ctx->device = device;
-    CK(cudaSetDevice(device));
-    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    CKC(cudaSetDevice(device));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     if (const char* v = getenv("PTB_TRACE_OVERLAP")) ctx->overlap_enabled = atoi(v) != 0;     // A/B switch for tools/, default on
     cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
+    CKC(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
 
     Frame& F = ctx->F;
@@ -274,27 +278,27 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
 
     if (dev_alloc(ctx, &F.counters, 1) || dev_alloc(ctx, &F.totals, 1) || dev_alloc(ctx, &F.trace_stats, 2)) { ptb_destroy(ctx); return PTB_E_STATE; }
     if (dev_alloc(ctx, &F.bin_counts, PTB_ORDER_MAX_BOUNCE * 2 * PTB_ORDER_MAX_BINS)) { ptb_destroy(ctx); return PTB_E_STATE; }
-    CK(cudaMemsetAsync(F.bin_counts, 0, sizeof(int) * PTB_ORDER_MAX_BOUNCE * 2 * PTB_ORDER_MAX_BINS, ctx->stream));
+    CKC(cudaMemsetAsync(F.bin_counts, 0, sizeof(int) * PTB_ORDER_MAX_BOUNCE * 2 * PTB_ORDER_MAX_BINS, ctx->stream));
     F.order_bins = PTB_DEFAULT_ORDER_BINS;
-    CK(cudaMemsetAsync(F.trace_stats, 0, 2 * sizeof(TraceStats), ctx->stream));
-    CK(cudaMemsetAsync(F.counters, 0, sizeof(Counters), ctx->stream));
-    CK(cudaMemsetAsync(F.totals, 0, sizeof(RayTotals), ctx->stream));
+    CKC(cudaMemsetAsync(F.trace_stats, 0, 2 * sizeof(TraceStats), ctx->stream));
+    CKC(cudaMemsetAsync(F.counters, 0, sizeof(Counters), ctx->stream));
+    CKC(cudaMemsetAsync(F.totals, 0, sizeof(RayTotals), ctx->stream));
     const size_t pixels = (size_t)F.pitch * F.height;
     F.fb_stride = (int)pixels;
     F.pix_bits = 1; while ((1ull << F.pix_bits) < pixels) F.pix_bits++;
     F.wave_samples = 1; F.first_sample = 0;
     if (dev_alloc(ctx, &F.display, pixels) || dev_alloc(ctx, &ctx->tap_hits, pixels) || dev_alloc(ctx, &F.pixel_query, 4)) { ptb_destroy(ctx); return PTB_E_STATE; }
-    CK(cudaMemsetAsync(F.pixel_query, 0xff, 4 * sizeof(int), ctx->stream));      // {INVALID, INVALID, INVALID}: no query pending
-    CK(cudaMemsetAsync(F.display, 0, pixels * sizeof(float4), ctx->stream));
+    CKC(cudaMemsetAsync(F.pixel_query, 0xff, 4 * sizeof(int), ctx->stream));      // {INVALID, INVALID, INVALID}: no query pending
+    CKC(cudaMemsetAsync(F.display, 0, pixels * sizeof(float4), ctx->stream));
     F.config.aov_mask = 1u;          // RADIANCE is always on (Pathtracer.cpp:267-268)
     { int e = allocate_wave_storage(ctx, 1); if (e) { ptb_destroy(ctx); return e; } }
 
     preload_kernels();
-    CK(cudaFuncSetAttribute(k_trace8<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CK(cudaFuncSetAttribute(k_trace8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CK(cudaFuncSetAttribute(k_trace8<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CK(cudaFuncSetAttribute(k_trace8<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CKC(cudaFuncSetAttribute(k_trace8<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return 0;
 }
@@ -463,7 +467,8 @@ static int bake_luts(ptb_ctx* ctx) {
     if (ctx->luts_ready) return 0;
     Frame& F = ctx->F;
     const int D = PTB_LUT_DIELECTRIC_DIM, C = PTB_LUT_CONDUCTOR_DIM;
-    float *dir = nullptr, *avg = nullptr;
+    float *dir = nullptr, *avg = nullptr, *cdir = nullptr, *cavg = nullptr;
+    struct Scratch { float **a, **b, **c, **d; ~Scratch() { cudaFree(*a); cudaFree(*b); cudaFree(*c); cudaFree(*d); } } scratch{ &dir, &avg, &cdir, &cavg };
     CK(cudaMalloc(&dir, sizeof(float) * D * D * D));
     CK(cudaMalloc(&avg, sizeof(float) * D * D));
     cudaTextureObject_t* dir_tex[2] = { &F.lut_dielectric_dir_enter, &F.lut_dielectric_dir_leave };
@@ -477,7 +482,6 @@ static int bake_luts(ptb_ctx* ctx) {
         int e = create_float_texture(ctx, &ctx->lut_arrays[pass], dir_tex[pass], dir, 1, D, D, D, true); if (e) return e;
         e = create_float_texture(ctx, &ctx->lut_arrays[2 + pass], avg_tex[pass], avg, 1, D, D, 0, true); if (e) return e;
     }
-    float *cdir = nullptr, *cavg = nullptr;
     CK(cudaMalloc(&cdir, sizeof(float) * C * C));
     CK(cudaMalloc(&cavg, sizeof(float) * C));
     k_integrate_conductor<<<(C * C + 255) / 256, 256, 0, ctx->stream>>>(F, cdir);
@@ -486,7 +490,6 @@ static int bake_luts(ptb_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     int e = create_float_texture(ctx, &ctx->lut_arrays[4], &F.lut_conductor_dir, cdir, 1, C, C, 0, true); if (e) return e;
     e = create_float_texture(ctx, &ctx->lut_arrays[5], &F.lut_conductor, cavg, 1, C, 0, 0, true); if (e) return e;
-    cudaFree(dir); cudaFree(avg); cudaFree(cdir); cudaFree(cavg);
     ctx->luts_ready = true;
     return 0;
 }
@@ -578,6 +581,13 @@ static int upload_pruned_tlas(ptb_ctx* ctx) {
     return stage_upload(ctx, ctx->merge_nodes, tl.data(), tl.size());
 }
 
+static std::vector<int> identity_roots_sorted(const std::vector<int>& roots) {
+    std::vector<int> r;
+    for (int v : roots) if ((unsigned)v & PTB_ROOT_IDENTITY) r.push_back(v);
+    std::sort(r.begin(), r.end());
+    return r;
+}
+
 static int rebuild_static_merge(ptb_ctx* ctx) {
     Frame& F = ctx->F;
     drop_graphs(ctx);
@@ -589,6 +599,7 @@ static int rebuild_static_merge(ptb_ctx* ctx) {
         for (int i = 0; i < M; i++) if ((unsigned)ctx->host_roots[i] & PTB_ROOT_IDENTITY) slots.push_back(i);
     std::vector<int> device_roots = ctx->host_roots;
     ctx->merge_slot_root.clear(); ctx->merge_slot_instance.clear();
+    ctx->merge_decided_roots = identity_roots_sorted(ctx->host_roots);
     if (ctx->merge_nodes) { cudaFree(ctx->merge_nodes); ctx->merge_nodes = nullptr; }
     if (ctx->merge_tris) { cudaFree(ctx->merge_tris); ctx->merge_tris = nullptr; }
     if (ctx->merge_slot_instance_dev) { cudaFree(ctx->merge_slot_instance_dev); ctx->merge_slot_instance_dev = nullptr; }
@@ -662,6 +673,11 @@ static int apply_roots(ptb_ctx* ctx, const int32_t* roots, int mesh_count) {
     if (ctx->bvh_kind != 8) { std::vector<int> r = ctx->host_roots; upload_roots(ctx, r); return 0; }
     std::vector<int> ident;
     for (int i = 0; i < mesh_count; i++) if ((unsigned)roots[i] & PTB_ROOT_IDENTITY) ident.push_back(i);
+    // Nothing is merged (merge switched off, skipped as too deep, or no identity instance) and the set of identity instances is the
+    // one that decision was taken on: the roots go up as they are -- no rebuild, no stream synchronise, the frame graphs survive.
+    if (ctx->merge_slot_root.empty() && identity_roots_sorted(ctx->host_roots) == ctx->merge_decided_roots) {
+        std::vector<int> r = ctx->host_roots; upload_roots(ctx, r); return 0;
+    }
     bool same = ctx->merge_enabled && ident.size() == ctx->merge_slot_root.size();
     std::vector<int> slot_instance(ctx->merge_slot_root.size(), -1);
     if (same) {
@@ -695,6 +711,13 @@ extern "C" int ptb_upload_scene(ptb_ctx* ctx, const ptb_scene* s) {
     if (ctx->has_scene) return PTB_E_STATE;     // one scene per ctx (create a new ctx to switch scenes)
     if (!s->triangles || !s->bvh_nodes || s->mesh_count <= 0 || (s->bvh_kind != 8 && s->bvh_kind != 2) || !s->pmj_samples || !s->blue_noise || !s->sky)
         return PTB_E_BADARG;
+    // layout convention of the node array (Integrator.cpp:113,252-277): TLAS in slots [0, 2 * mesh_count), every BLAS root behind it --
+    // ptb_update_instances overwrites the front of the array and relies on it
+    if (s->tlas_node_count < 0 || s->tlas_node_count > 2 * s->mesh_count || s->bvh_node_count < 2 * s->mesh_count) return PTB_E_BADARG;
+    for (int i = 0; i < s->mesh_count; i++) {
+        unsigned root = (unsigned)s->mesh_bvh_root_indices[i] & 0x3fffffffu;
+        if (root < 2u * (unsigned)s->mesh_count || root >= (unsigned)s->bvh_node_count) return PTB_E_BADARG;
+    }
     CK(cudaSetDevice(ctx->device));
     { int de = load_driver_api(); if (de) return de; }
     Frame& F = ctx->F;
@@ -844,7 +867,8 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
         { StageTimer t(ctx, ST_TRACE);
           if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<false, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order_c);
                                     else                 k_trace8<false, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order_c); }
-          else                    k_trace2<false><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
+          else if (ctx->stats_mode) k_trace2<false, true><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
+          else                    k_trace2<false, false><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
           ctx->launches++; }
         if (side_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); side_pending = false; }     // shadow[bounce-1] deposits before sort[bounce]
         { StageTimer t(ctx, ST_SORT); k_sort<<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
@@ -861,7 +885,8 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
             if (overlap) { CK(cudaEventRecord(ctx->ev_fork, st)); CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0)); ss = ctx->side_stream; }
             if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<true, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), ss>>>(F, bounce, order_s);
                                       else                 k_trace8<true, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), ss>>>(F, bounce, order_s); }
-            else                    k_trace2<true><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce);
+            else if (ctx->stats_mode) k_trace2<true, true><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce);
+            else                    k_trace2<true, false><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce);
             ctx->launches++;
             if (overlap) { CK(cudaEventRecord(ctx->ev_join, ctx->side_stream)); side_pending = true; }
         }
@@ -1042,7 +1067,6 @@ extern "C" int ptb_exchange_frame(ptb_ctx* ctx, void** device_ptr, int* pitch) {
 extern "C" int ptb_measure_traversal(ptb_ctx* ctx, int sample_index, ptb_traversal_stats* out) {
     if (!ctx || !out) return PTB_E_BADARG;
     if (!ctx->has_scene) return PTB_E_NOSCENE;
-    if (ctx->bvh_kind != 8) return PTB_E_STATE;
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(ctx->F.trace_stats, 0, 2 * sizeof(TraceStats), ctx->stream));
     ctx->stats_mode = true;

@@ -396,7 +396,7 @@ PTB_DI bool node2_hit(float4 a, float4 b, const Ray& ray, float tmax) {
     return tn < tf;
 }
 
-template <bool SHADOW>
+template <bool SHADOW, bool STATS>
 __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace2(const __grid_constant__ Frame P, int bounce) {
     const int count = SHADOW ? P.counters->shadow[bounce] : P.counters->trace[bounce];
     int* retired = SHADOW ? &P.counters->retired_shadow[bounce] : &P.counters->retired[bounce];
@@ -404,14 +404,23 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
     const unsigned lane = threadIdx.x & 31u;
     const unsigned FULL = 0xffffffffu;
     int stack[PTB_STACK_TOTAL];
+    unsigned long long st_nodes = 0, st_tris = 0, st_xf = 0, st_rays = 0, st_miss = 0;
     while (true) {
         // one ray per lane per round; refill is warp-aggregated
         int base = 0;
         if (lane == 0) base = atomicAdd(retired, 32);
         base = __shfl_sync(FULL, base, 0);
-        if (base >= count) return;
+        if (base >= count) {
+            if (STATS) {      // roofline accounting (32-byte nodes, 48-byte triangle tests), same counters as k_trace8<*, true>
+                TraceStats* ts = P.trace_stats + (SHADOW ? 1 : 0);
+                atomicAdd(&ts->nodes, st_nodes); atomicAdd(&ts->triangles, st_tris); atomicAdd(&ts->instance_transforms, st_xf);
+                atomicAdd(&ts->rays, st_rays); atomicAdd(&ts->misses, st_miss);
+            }
+            return;
+        }
         int ray_index = base + int(lane);
         if (ray_index >= count) continue;
+        if (STATS) st_rays++;
         float4 a = SHADOW ? P.sq.od0[ray_index] : q.od0[ray_index];
         float4 b = SHADOW ? P.sq.od1[ray_index] : q.od1[ray_index];
         Ray world; world.o = f3(a.x, a.y, a.z); world.d = f3(a.w, b.x, b.y);
@@ -424,6 +433,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
             if (sp == tlas_sp) { tlas_sp = PTB_INVALID; if (!identity) ray = world; }
             int ni = stack[--sp];
             float4 na = __ldg(P.nodes2 + 2 * size_t(ni)), nb = __ldg(P.nodes2 + 2 * size_t(ni) + 1);
+            if (STATS) st_nodes++;
             if (!node2_hit(na, nb, ray, hit.t)) continue;
             int first = __float_as_int(nb.z);
             unsigned count_axis = __float_as_uint(nb.w);
@@ -437,10 +447,12 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                     if (!identity) {
                         Mat3x4 inv = load_mat(P.mesh_transforms_inv, mesh_id);
                         ray.o = xform_pos(inv, ray.o); ray.d = xform_dir(inv, ray.d);
+                        if (STATS) st_xf++;
                     }
                     stack[sp++] = int(root & 0x7fffffffu);
                 } else {
                     for (int t = first; t < first + int(n); t++) {
+                        if (STATS) st_tris++;
                         if (SHADOW) { if (occludes_triangle(P, mesh_id, t, ray, hit.t)) { occluded = true; break; } }
                         else intersect_triangle(P, mesh_id, t, ray, hit);
                     }
@@ -454,6 +466,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
         }
         if (SHADOW) {
             if (!occluded) {
+                if (STATS) st_miss++;
                 float4 ill = P.sq.illum[ray_index];
                 int px = word_fb_index(P, __float_as_uint(b.w));
                 float4 v = make_float4(ill.x, ill.y, ill.z, 0.0f);
@@ -605,7 +618,7 @@ __global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, i
                 ended = true;
             }
             if (!ended) {
-                if (bounce == 0 && P.pixel_query[0] == pixel_index) {     // GUI picking (Pathtracer.cu:345-348); pixel_index is -1 unless a query is pending
+                if (bounce == 0 && P.pixel_query[0] == pixel_index && word_slot(P, pf) == 0) {     // GUI picking (Pathtracer.cu:345-348); pixel_index is -1 unless a query is pending
                     P.pixel_query[1] = hit.mesh_id; P.pixel_query[2] = hit.triangle_id;
                 }
                 int material_id = P.mesh_material_ids[hit.mesh_id];

@@ -202,6 +202,7 @@ class Pathtracer:
         scene = fill_scene_struct(blob, keep)
         _check(l.ptb_upload_scene(self._ctx, ctypes.byref(scene)), "ptb_upload_scene")
         self.gpu_config = config or default_config(num_bounces=int(blob["num_bounces"]))
+        self._instance_order = np.asarray(blob["instance_order"]) if "instance_order" in blob else None
         self._camera = camera_struct(blob["camera"])
         self._view_projection = np.ascontiguousarray(blob["view_projection"], dtype=np.float32)
         self._view_projection_prev = self._view_projection.copy()
@@ -317,11 +318,16 @@ class Pathtracer:
         """Integrator::set_pixel_query (Integrator.h:266-277): the next pass records what the primary ray of pixel (x, y) hits."""
         _check(lib().ptb_set_pixel_query(self._ctx, int(x), int(y)), "ptb_set_pixel_query")
 
-    def get_pixel_query(self):
-        """(mesh_id, triangle_id) of the pending query, (-1, -1) for sky; clears the query."""
+    def get_pixel_query(self, scene_index=False):
+        """(mesh_id, triangle_id) of the pending query, (-1, -1) for sky (or when another rank owns the pixel's row); clears the
+        query.  mesh_id is the instance index in TLAS leaf order -- the index every device table uses; scene_index=True maps it
+        back to the scene's mesh index through the TLAS leaf order like Integrator::update does (Integrator.cpp:486-488)."""
         m, t = ctypes.c_int(), ctypes.c_int()
         _check(lib().ptb_get_pixel_query(self._ctx, ctypes.byref(m), ctypes.byref(t)), "ptb_get_pixel_query")
-        return m.value, t.value
+        mesh = m.value
+        if scene_index and mesh >= 0 and self._instance_order is not None:
+            mesh = int(self._instance_order[mesh])
+        return mesh, t.value
 
     def set_static_merge(self, enabled):
         """include/ptb.h: ptb_set_static_merge (identity-transform instances traced through one merged CWBVH)."""

@@ -585,6 +585,43 @@ def view_projection(position, rotation, fov, width, height, near=0.1, far=300.0)
     return (p @ m_rotation(q_conj(rotation)) @ m_translate(-np.asarray(position))).astype(f32).reshape(-1)
 
 
+def camera_params_of(blob):
+    """(position, rotation matrix 3x3, tan(fov/2), aperture, focal) recovered from a blob's 15-float camera block + film size."""
+    cam = np.asarray(blob["camera"], dtype=np.float64)
+    w0 = float(blob["width"])
+    pos, blc, xa, ya = cam[0:3], cam[3:6], cam[6:9], cam[9:12]
+    za = np.cross(xa, ya)
+    d0 = -float(np.dot(blc, za))
+    return pos.copy(), np.stack([xa, ya, za], axis=1), (0.5 * w0) / d0, float(cam[13]), float(cam[14])
+
+
+def retarget_blob(blob, width, height, forward=None, fov=None):
+    """Same scene, another film size (and optionally another view direction / fov): recomputes the camera block and the
+    view-projection matrix (Camera::resize -> recalibrate, Src/Renderer/Camera.cpp:10-42); everything else is shared.
+    `forward` = world-space viewing direction (the camera looks along its local -z)."""
+    out = dict(blob)
+    pos, R, tan_half, aperture, focal = camera_params_of(blob)
+    if fov is not None:
+        tan_half = math.tan(0.5 * fov)
+    if forward is not None:
+        rot = q_look_rotation(tuple(-np.asarray(forward, dtype=np.float64)), (0.0, 1.0, 0.0))
+        R = m_rotation(rot)[:3, :3]
+    half_w, half_h = 0.5 * width, 0.5 * height
+    d = half_w / tan_half
+    blc = R @ np.array([-half_w, -half_h, -d])
+    spread = math.atan(2.0 * tan_half / width)
+    out["camera"] = np.array(list(pos) + list(blc) + list(R[:, 0]) + list(R[:, 1]) + [spread, aperture, focal], dtype=f32)
+    near, far = 0.1, 300.0
+    p = np.zeros((4, 4))
+    p[0, 0] = 1.0 / tan_half; p[1, 1] = 1.0 / ((half_h / half_w) * tan_half)
+    p[2, 2] = -(far + near) / (far - near); p[3, 2] = -1.0
+    p[2, 3] = -2.0 * (far * near) / (far - near)
+    view = np.eye(4); view[:3, :3] = R.T; view[:3, 3] = -(R.T @ pos)
+    out["view_projection"] = (p @ view).astype(f32).reshape(-1)
+    out["width"], out["height"] = int(width), int(height)
+    return out
+
+
 def pack_triangles(p, n, t):
     out = np.empty((p.shape[0], 24), dtype=f32)
     out[:, 0:3] = p[:, 0]; out[:, 3:6] = p[:, 1] - p[:, 0]; out[:, 6:9] = p[:, 2] - p[:, 0]

@@ -8,11 +8,18 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CUBIN = os.path.join(_HERE, "_ref", "pathtracer_ref.cubin")
+# the same source with the documented one-function patch of oracle/patch_uniform_lut.py (warp-uniform LUT handles): the checker
+# for the rough-dielectric BSDF, where the unmodified build is miscompiled by ptxas 12.9
+CUBIN_UNIFORM = os.path.join(_HERE, "_ref", "pathtracer_ref_uniform.cubin")
 _lib = None
 
 
 def available():
     return os.path.exists(CUBIN)
+
+
+def uniform_available():
+    return os.path.exists(CUBIN_UNIFORM)
 
 
 def lib():
@@ -29,14 +36,14 @@ def lib():
 class Reference:
     """Same surface as gpu_raytracer_b200.pathtracer.Pathtracer (render_pass / get_aov / ray_stats ...)."""
 
-    def __init__(self, blob, config=None, device=0):
+    def __init__(self, blob, config=None, device=0, cubin=None):
         from gpu_raytracer_b200 import pathtracer as pt   # only for the plain ctypes struct definitions of include/ptb.h
         self._pt = pt
         l = lib()
         self.width, self.height = int(blob["width"]), int(blob["height"])
         self.pitch = (self.width + 31) // 32 * 32
         self._ctx = ctypes.c_void_p()
-        self._ck(l.ref_create(ctypes.byref(self._ctx), CUBIN.encode(), device, self.width, self.height), "ref_create")
+        self._ck(l.ref_create(ctypes.byref(self._ctx), (cubin or CUBIN).encode(), device, self.width, self.height), "ref_create")
         keep = []
         scene = pt.fill_scene_struct(blob, keep)
         self._ck(l.ref_upload_scene(self._ctx, ctypes.byref(scene)), "ref_upload_scene")
@@ -97,6 +104,17 @@ class Reference:
         l = lib(); l.ref_read_global_buffer.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
         self._ck(l.ref_read_global_buffer(self._ctx, name.encode(), ctypes.c_void_p(out.ctypes.data), out.nbytes), "ref_read_global_buffer")
         return out
+
+    def begin_display_download(self, slot):
+        """queue the pipelined device->host read of the displayed frame into pinned slot 0/1 (bench.py e2e leg)"""
+        self._ck(lib().ref_e2e_begin_download(self._ctx, int(slot)), "ref_e2e_begin_download")
+
+    def wait_display_download(self, slot):
+        """block until slot's read-back has landed; returns it as a [height, pitch, 4] float32 view of the pinned buffer"""
+        p = ctypes.c_void_p()
+        self._ck(lib().ref_e2e_wait(self._ctx, int(slot), ctypes.byref(p)), "ref_e2e_wait")
+        n = self.height * self.pitch * 4
+        return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_float)), shape=(n,)).reshape(self.height, self.pitch, 4)
 
     def lut_contents(self):
         n = 2 * 16 ** 3 + 2 * 16 ** 2 + 32 ** 2 + 32

@@ -66,6 +66,11 @@ struct ref_ctx {
     std::vector<CUevent> events; size_t ev_used = 0;
     std::vector<std::pair<int, std::pair<CUevent, CUevent>>> timed;
     float stage_ms[6] = {};
+    // end-to-end read-back of the display surface, double-buffered like the product arm's (bench.py --impl reference)
+    CUstream copy_stream = nullptr;
+    CUdeviceptr e2e_stage[2] = {};
+    void* e2e_host[2] = {};
+    CUevent e2e_rendered[2] = {}, e2e_done[2] = {};
 };
 
 static int get_global(ref_ctx* c, const char* name, CUdeviceptr* p, size_t* sz) {
@@ -158,6 +163,8 @@ void ref_destroy(ref_ctx* c) {
     if (c->surf) cuSurfObjectDestroy(c->surf);
     if (c->surf_array) cuArrayDestroy(c->surf_array);
     for (CUevent e : c->events) cuEventDestroy(e);
+    for (int k = 0; k < 2; k++) { if (c->e2e_host[k]) cuMemFreeHost(c->e2e_host[k]); if (c->e2e_rendered[k]) cuEventDestroy(c->e2e_rendered[k]); if (c->e2e_done[k]) cuEventDestroy(c->e2e_done[k]); }
+    if (c->copy_stream) cuStreamDestroy(c->copy_stream);
     if (c->mod) cuModuleUnload(c->mod);
     delete c;
 }
@@ -598,6 +605,38 @@ int ref_read_global_buffer(ref_ctx* c, const char* global_name, void* dst, size_
     RCK(cuMemcpyDtoH(&p, g, sizeof(p)));
     if (!p) return 1;
     RCK(cuMemcpyDtoH(dst, p, bytes));
+    return 0;
+}
+
+// Pipelined read-back of the displayed frame (what bench.py's e2e leg does for the product arm): the display surface is parked in
+// a linear staging buffer on the render stream (device to device), then copied to pinned host memory on a separate non-blocking
+// stream while the next frame renders.  ref_e2e_wait(slot) blocks until that copy has landed and returns the host pointer.
+int ref_e2e_begin_download(ref_ctx* c, int slot) {
+    RCK(cuCtxSetCurrent(c->cu));
+    if (slot < 0 || slot > 1) return 1;
+    const size_t bytes = (size_t)c->pitch * c->height * 16;
+    if (!c->copy_stream) RCK(cuStreamCreate(&c->copy_stream, CU_STREAM_NON_BLOCKING));
+    if (!c->e2e_stage[slot]) {
+        RCK(cuMemAlloc(&c->e2e_stage[slot], bytes)); c->allocs.push_back(c->e2e_stage[slot]);
+        RCK(cuMemAllocHost(&c->e2e_host[slot], bytes));
+        RCK(cuEventCreate(&c->e2e_rendered[slot], CU_EVENT_DISABLE_TIMING));
+        RCK(cuEventCreate(&c->e2e_done[slot], CU_EVENT_DISABLE_TIMING));
+    }
+    CUDA_MEMCPY2D cp; memset(&cp, 0, sizeof(cp));
+    cp.srcMemoryType = CU_MEMORYTYPE_ARRAY; cp.srcArray = c->surf_array; cp.dstMemoryType = CU_MEMORYTYPE_DEVICE; cp.dstDevice = c->e2e_stage[slot];
+    cp.dstPitch = (size_t)c->pitch * 16; cp.WidthInBytes = cp.dstPitch; cp.Height = c->height;
+    RCK(cuMemcpy2DAsync(&cp, nullptr));
+    RCK(cuEventRecord(c->e2e_rendered[slot], nullptr));
+    RCK(cuStreamWaitEvent(c->copy_stream, c->e2e_rendered[slot], 0));
+    RCK(cuMemcpyDtoHAsync(c->e2e_host[slot], c->e2e_stage[slot], bytes, c->copy_stream));
+    RCK(cuEventRecord(c->e2e_done[slot], c->copy_stream));
+    return 0;
+}
+int ref_e2e_wait(ref_ctx* c, int slot, void** host_ptr) {
+    RCK(cuCtxSetCurrent(c->cu));
+    if (slot < 0 || slot > 1 || !c->e2e_done[slot]) return 1;
+    RCK(cuEventSynchronize(c->e2e_done[slot]));
+    if (host_ptr) *host_ptr = c->e2e_host[slot];
     return 0;
 }
 

@@ -13,13 +13,14 @@ from gpu_raytracer_b200 import pathtracer as pt, scene  # noqa: E402
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(rank)
+    device = rank % torch.cuda.device_count()          # a 1-GPU box: both processes share the GPU (CUDA IPC works within a device too)
+    torch.cuda.set_device(device)
     dist.init_process_group("gloo")
     d = scene.procedural_scene("atrium", seed=9, width=416, height=250, detail=0.5)
     blob = scene.build_blob(d, 8, rng="fallback")
     cfg = pt.default_config(num_bounces=3)
-    whole = pt.Pathtracer(blob, device=rank, config=cfg)
-    p = pt.Pathtracer(blob, device=rank, rank=rank, world=world, band_rows=8, config=cfg)
+    whole = pt.Pathtracer(blob, device=device, config=cfg)
+    p = pt.Pathtracer(blob, device=device, rank=rank, world=world, band_rows=8, config=cfg)
     p.reserve_wave(5)
     _, handle = p.exchange_create()
     handles = [None] * world

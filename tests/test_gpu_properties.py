@@ -199,9 +199,9 @@ def test_peer_memory_exchange_times_out_instead_of_hanging():
     a.close(); b.close()
 
 
-@pytest.mark.skipif(__import__("torch").cuda.device_count() < 2, reason="needs 2 GPUs (CUDA IPC between two processes)")
 def test_peer_memory_exchange_between_processes():
-    """Two processes, one GPU each, blocks connected through CUDA IPC handles: both end up with the 1-GPU frame."""
+    """Two processes (one GPU each when the box has two, otherwise sharing GPU 0), blocks connected through CUDA IPC handles:
+    both end up with the 1-GPU frame.  This is the data plane bench.py --gpus N rides on."""
     import subprocess, sys
     worker = os.path.join(os.path.dirname(__file__), "_exchange_worker.py")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
