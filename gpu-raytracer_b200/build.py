@@ -2,6 +2,7 @@
 
   build_host()   -> gpu-raytracer_b200/host/libptb_host.so   C++ CPU BVH builder (SAH + CWBVH)
   build_cuda()   -> gpu-raytracer_b200/csrc/libptb.so        sm_100a kernels + the C ABI of include/ptb.h
+  build_facade() -> gpu-raytracer_b200/host/libptb_pathtracer.so  compiled C++ facade (Integrator / Pathtracer entry points) + tests/cpp/facade_render
   build_oracle() -> oracle/libpt_oracle.so                    CPU restatement (test infrastructure only)
   build_ref()    -> oracle/_ref/*                             reference kernels compiled from /root/reference (if present)
 """
@@ -35,7 +36,7 @@ def build_host(force=False):
     src = os.path.join(PKG_DIR, "host", "bvh_build.cpp")
     out = os.path.join(PKG_DIR, "host", "libptb_host.so")
     if force or _stale(out, [src, os.path.join(PKG_DIR, "host", "static_merge.h")]):
-        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", out, src])
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-pthread", "-o", out, src])
     return out
 
 
@@ -59,6 +60,24 @@ def build_cuda(force=False, verbose=False, defines=(), suffix=""):
         log = _run(cmd)
         if verbose:
             print(log)
+    return out
+
+
+def build_facade(force=False):
+    """host/libptb_pathtracer.so: the compiled C++ facade (Integrator / Pathtracer entry points over the C ABI), and the small
+    test driver tests/cpp/facade_render that renders through it."""
+    src = os.path.join(PKG_DIR, "host", "ptb_pathtracer.cpp")
+    hdr = os.path.join(PKG_DIR, "host", "ptb_pathtracer.h")
+    out = os.path.join(PKG_DIR, "host", "libptb_pathtracer.so")
+    libdir = os.path.join(PKG_DIR, "csrc")
+    inc = ["-I", os.path.join(REPO_ROOT, "include"), "-I", os.path.join(PKG_DIR, "host")]
+    if force or _stale(out, [src, hdr, os.path.join(REPO_ROOT, "include", "ptb.h")]):
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", *inc, "-o", out, src, "-L", libdir, "-lptb", "-Wl,-rpath,$ORIGIN/../csrc"])
+    drv_src = os.path.join(REPO_ROOT, "tests", "cpp", "facade_render.cpp")
+    drv = os.path.join(REPO_ROOT, "tests", "cpp", "facade_render")
+    if force or _stale(drv, [drv_src, hdr, out]):
+        _run(["g++", "-O2", "-std=c++17", *inc, "-o", drv, drv_src, "-L", os.path.join(PKG_DIR, "host"), "-lptb_pathtracer", "-L", libdir, "-lptb",
+              "-Wl,-rpath,$ORIGIN/../../gpu-raytracer_b200/host", "-Wl,-rpath,$ORIGIN/../../gpu-raytracer_b200/csrc", "-Wl,-rpath-link," + libdir])
     return out
 
 

@@ -69,6 +69,7 @@ struct ptb_ctx {
     int  sm_count = 148;
     int  owned_rows = 0;
     std::vector<void*> allocs;       // everything cudaMalloc'ed, freed in ptb_destroy
+    std::vector<void*> film_allocs;  // everything sized by the film (display, accumulators, SVGF state): re-allocated by ptb_resize
     std::vector<void*> wave_allocs;  // ray queues + framebuffer planes, re-allocated by ptb_reserve_wave
     int wave_capacity = 1;           // pass slots a wave can carry
     std::vector<DeviceTexture> textures;
@@ -98,6 +99,7 @@ struct ptb_ctx {
     bool overlap_enabled = true;
     // static merge: identity-transform instances re-built into ONE CWBVH at upload (rebuild_static_merge)
     bool merge_enabled = true;
+    bool merge_spatial = true;                        // merged BVH built with spatial splits (SBVH); false = plain full-sweep SAH
     std::vector<unsigned char> host_nodes;            // node array as uploaded by the host (for leaf walks)
     std::vector<float4> host_tri_pos;                 // first 3 float4 of every triangle record
     std::vector<int> host_roots;                      // roots as last given by the host
@@ -106,6 +108,9 @@ struct ptb_ctx {
     std::vector<int> merge_decided_roots;             // sorted roots of the identity instances the last merge decision (built, disabled or skipped) was taken on
     float4* merge_nodes = nullptr;                    // device: [host node array | merged nodes], owned
     float4* merge_tris = nullptr;
+    float4* merge_woop = nullptr;                     // Woop maps of the merged references (ptb_set_intersector)
+    int2*   merge_who = nullptr;
+    int     intersector = PTB_INTERSECT_MT;
     int*    merge_slot_instance_dev = nullptr;
     const float4* uploaded_nodes = nullptr;           // device copy of the host's array (kept: the fallback when nothing is merged)
     // pinned staging for the per-frame uploads (ptb_update_instances): the host arrays are copied here during the call and the
@@ -125,6 +130,7 @@ struct ptb_ctx {
 // CPU SAH + CWBVH builder (host/bvh_build.cpp, linked into this library): used for the merged static BVH
 extern "C" {
 void* ptbh_build_triangles(const float* pos, int n, int kind, float sah_node, float sah_leaf);
+void* ptbh_build_triangles_sbvh(const float* pos, int n, float alpha, int bins, float max_dup);
 int   ptbh_node_count(void* h);
 int   ptbh_index_count(void* h);
 void  ptbh_export(void* h, void* nodes_out, int* indices_out, int node_offset, int index_offset);
@@ -149,6 +155,14 @@ static int dev_alloc(ptb_ctx* ctx, T** out, size_t count) {
     void* p = nullptr;
     CK(cudaMalloc(&p, (count ? count : 1) * sizeof(T)));
     ctx->allocs.push_back(p);
+    *out = static_cast<T*>(p);
+    return 0;
+}
+template <typename T>
+static int film_alloc(ptb_ctx* ctx, T** out, size_t count) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, (count ? count : 1) * sizeof(T)));
+    ctx->film_allocs.push_back(p);
     *out = static_cast<T*>(p);
     return 0;
 }
@@ -200,10 +214,29 @@ static int allocate_wave_storage(ptb_ctx* ctx, int samples) {
         if (!(F.config.aov_mask & (1u << k))) { F.aov[k].fb = nullptr; continue; }
         e |= wave_alloc(ctx, &F.aov[k].fb, plane * samples);
         if (!e) CK(cudaMemsetAsync(F.aov[k].fb, 0, plane * samples * sizeof(float4), ctx->stream));
-        if (!F.aov[k].acc) { e |= dev_alloc(ctx, &F.aov[k].acc, plane); if (!e) CK(cudaMemsetAsync(F.aov[k].acc, 0, plane * sizeof(float4), ctx->stream)); }
+        if (!F.aov[k].acc) { e |= film_alloc(ctx, &F.aov[k].acc, plane); if (!e) CK(cudaMemsetAsync(F.aov[k].acc, 0, plane * sizeof(float4), ctx->stream)); }
     }
     if (e) return PTB_E_STATE;
     ctx->wave_capacity = samples;
+    return 0;
+}
+
+// Everything whose size follows the film (the role of Pathtracer::resize_init, Pathtracer.cpp:255-301): display image, hit tap,
+// accumulators, wave storage, SVGF state.  F.width / F.height must be set; called by ptb_create and ptb_resize.
+static int ensure_svgf(ptb_ctx* ctx);
+static int allocate_film(ptb_ctx* ctx) {
+    Frame& F = ctx->F;
+    F.pitch = (F.width + 31) / 32 * 32;
+    ctx->owned_rows = owned_rows_of(F.height, F.rank, F.world, F.band_rows);
+    F.local_pixels = ctx->owned_rows * F.width;
+    const size_t pixels = (size_t)F.pitch * F.height;
+    F.fb_stride = (int)pixels;
+    F.pix_bits = 1; while ((1ull << F.pix_bits) < pixels) F.pix_bits++;
+    F.wave_samples = 1; F.first_sample = 0;
+    if (film_alloc(ctx, &F.display, pixels) || film_alloc(ctx, &ctx->tap_hits, pixels)) return PTB_E_STATE;
+    CK(cudaMemsetAsync(F.display, 0, pixels * sizeof(float4), ctx->stream));
+    int e = allocate_wave_storage(ctx, ctx->wave_capacity); if (e) return e;
+    if (F.config.enable_svgf) { e = ensure_svgf(ctx); if (e) return e; }
     return 0;
 }
 
@@ -264,10 +297,8 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
 
     Frame& F = ctx->F;
     memset(&F, 0, sizeof(F));
-    F.width = width; F.height = height; F.pitch = (width + 31) / 32 * 32;
+    F.width = width; F.height = height;
     F.rank = rank; F.world = world; F.band_rows = band_rows;
-    ctx->owned_rows = owned_rows_of(height, rank, world, band_rows);
-    F.local_pixels = ctx->owned_rows * width;
 
     // defaults of GPUConfig (Common.h:39-67)
     F.config.reconstruction_filter = 2; F.config.aov_mask = 1u; F.config.num_bounces = 10;
@@ -283,15 +314,11 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     CKC(cudaMemsetAsync(F.trace_stats, 0, 2 * sizeof(TraceStats), ctx->stream));
     CKC(cudaMemsetAsync(F.counters, 0, sizeof(Counters), ctx->stream));
     CKC(cudaMemsetAsync(F.totals, 0, sizeof(RayTotals), ctx->stream));
-    const size_t pixels = (size_t)F.pitch * F.height;
-    F.fb_stride = (int)pixels;
-    F.pix_bits = 1; while ((1ull << F.pix_bits) < pixels) F.pix_bits++;
-    F.wave_samples = 1; F.first_sample = 0;
-    if (dev_alloc(ctx, &F.display, pixels) || dev_alloc(ctx, &ctx->tap_hits, pixels) || dev_alloc(ctx, &F.pixel_query, 4)) { ptb_destroy(ctx); return PTB_E_STATE; }
+    if (dev_alloc(ctx, &F.pixel_query, 4)) { ptb_destroy(ctx); return PTB_E_STATE; }
     CKC(cudaMemsetAsync(F.pixel_query, 0xff, 4 * sizeof(int), ctx->stream));      // {INVALID, INVALID, INVALID}: no query pending
-    CKC(cudaMemsetAsync(F.display, 0, pixels * sizeof(float4), ctx->stream));
     F.config.aov_mask = 1u;          // RADIANCE is always on (Pathtracer.cpp:267-268)
-    { int e = allocate_wave_storage(ctx, 1); if (e) { ptb_destroy(ctx); return e; } }
+    ctx->wave_capacity = 1;
+    { int fe = allocate_film(ctx); if (fe) { ptb_destroy(ctx); return fe; } }
 
     preload_kernels();
     CKC(cudaFuncSetAttribute(k_trace8<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -315,6 +342,8 @@ extern "C" void ptb_destroy(ptb_ctx* ctx) {
     for (int c = 0; c < 2; c++) { if (ctx->stage_mem[c]) cudaFreeHost(ctx->stage_mem[c]); if (ctx->stage_dev[c]) cudaFree(ctx->stage_dev[c]); if (ctx->stage_done[c]) cudaEventDestroy(ctx->stage_done[c]); }
     if (ctx->merge_nodes) cudaFree(ctx->merge_nodes);
     if (ctx->merge_tris) cudaFree(ctx->merge_tris);
+    if (ctx->merge_woop) cudaFree(ctx->merge_woop);
+    if (ctx->merge_who) cudaFree(ctx->merge_who);
     if (ctx->merge_slot_instance_dev) cudaFree(ctx->merge_slot_instance_dev);
     if (g_drv.ok) for (auto& t : ctx->textures) { if (t.tex) g_drv.TexObjectDestroy(t.tex); if (t.array) g_drv.MipmappedArrayDestroy(t.array); }
     if (ctx->F.sky_tex) cudaDestroyTextureObject(ctx->F.sky_tex);
@@ -324,6 +353,7 @@ extern "C" void ptb_destroy(ptb_ctx* ctx) {
     for (int i = 0; i < 6; i++) { if (luts[i]) cudaDestroyTextureObject(luts[i]); if (ctx->lut_arrays[i]) cudaFreeArray(ctx->lut_arrays[i]); }
     drop_graphs(ctx);
     for (void* p : ctx->wave_allocs) cudaFree(p);
+    for (void* p : ctx->film_allocs) cudaFree(p);
     for (void* p : ctx->allocs) cudaFree(p);
     for (auto ev : ctx->event_pool) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -337,7 +367,7 @@ static int ensure_aov(ptb_ctx* ctx, int k) {
     const size_t plane = (size_t)F.pitch * F.height;
     int e = wave_alloc(ctx, &F.aov[k].fb, plane * ctx->wave_capacity); if (e) return e;
     CK(cudaMemsetAsync(F.aov[k].fb, 0, plane * ctx->wave_capacity * sizeof(float4), ctx->stream));
-    if (!F.aov[k].acc) { e = dev_alloc(ctx, &F.aov[k].acc, plane); if (e) return e; CK(cudaMemsetAsync(F.aov[k].acc, 0, plane * sizeof(float4), ctx->stream)); }
+    if (!F.aov[k].acc) { e = film_alloc(ctx, &F.aov[k].acc, plane); if (e) return e; CK(cudaMemsetAsync(F.aov[k].acc, 0, plane * sizeof(float4), ctx->stream)); }
     return 0;
 }
 
@@ -346,11 +376,11 @@ static int ensure_svgf(ptb_ctx* ctx) {
     if (F.svgf.history_length) return 0;
     const size_t pixels = (size_t)F.pitch * F.height;
     int e = 0;
-    e |= dev_alloc(ctx, &F.svgf.gbuf_normal_depth, pixels); e |= dev_alloc(ctx, &F.svgf.gbuf_ids, pixels); e |= dev_alloc(ctx, &F.svgf.gbuf_screen_prev, pixels);
-    e |= dev_alloc(ctx, &F.svgf.moment, pixels); e |= dev_alloc(ctx, &F.svgf.history_length, pixels);
-    e |= dev_alloc(ctx, &F.svgf.history_direct, pixels); e |= dev_alloc(ctx, &F.svgf.history_indirect, pixels);
-    e |= dev_alloc(ctx, &F.svgf.history_moment, pixels); e |= dev_alloc(ctx, &F.svgf.history_normal_depth, pixels);
-    e |= dev_alloc(ctx, &F.svgf.taa_prev, pixels); e |= dev_alloc(ctx, &F.svgf.taa_curr, pixels);
+    e |= film_alloc(ctx, &F.svgf.gbuf_normal_depth, pixels); e |= film_alloc(ctx, &F.svgf.gbuf_ids, pixels); e |= film_alloc(ctx, &F.svgf.gbuf_screen_prev, pixels);
+    e |= film_alloc(ctx, &F.svgf.moment, pixels); e |= film_alloc(ctx, &F.svgf.history_length, pixels);
+    e |= film_alloc(ctx, &F.svgf.history_direct, pixels); e |= film_alloc(ctx, &F.svgf.history_indirect, pixels);
+    e |= film_alloc(ctx, &F.svgf.history_moment, pixels); e |= film_alloc(ctx, &F.svgf.history_normal_depth, pixels);
+    e |= film_alloc(ctx, &F.svgf.taa_prev, pixels); e |= film_alloc(ctx, &F.svgf.taa_curr, pixels);
     if (e) return PTB_E_STATE;
     CK(cudaMemsetAsync(F.svgf.gbuf_normal_depth, 0, pixels * sizeof(float4), ctx->stream));
     CK(cudaMemsetAsync(F.svgf.gbuf_ids, 0, pixels * sizeof(int2), ctx->stream));
@@ -602,6 +632,9 @@ static int rebuild_static_merge(ptb_ctx* ctx) {
     ctx->merge_decided_roots = identity_roots_sorted(ctx->host_roots);
     if (ctx->merge_nodes) { cudaFree(ctx->merge_nodes); ctx->merge_nodes = nullptr; }
     if (ctx->merge_tris) { cudaFree(ctx->merge_tris); ctx->merge_tris = nullptr; }
+    if (ctx->merge_woop) { cudaFree(ctx->merge_woop); ctx->merge_woop = nullptr; }
+    if (ctx->merge_who) { cudaFree(ctx->merge_who); ctx->merge_who = nullptr; }
+    F.flat_woop = nullptr; F.flat_who = nullptr;
     if (ctx->merge_slot_instance_dev) { cudaFree(ctx->merge_slot_instance_dev); ctx->merge_slot_instance_dev = nullptr; }
     F.flat_root = -1; F.flat_all = 0; F.flat_node_count = 0; F.flat_tris = nullptr; F.flat_slot_instance = nullptr;
     if (ctx->bvh_kind == 8) F.nodes8 = ctx->uploaded_nodes;
@@ -626,26 +659,39 @@ static int rebuild_static_merge(ptb_ctx* ctx) {
     }
     const int n = (int)who.size();
     if (n == 0) { ctx->merge_slot_root.clear(); ctx->merge_slot_instance.clear(); upload_roots(ctx, ctx->host_roots); return 0; }
-    void* h = ptbh_build_triangles(pos.data(), n, 8, 4.0f, 1.0f);
-    if (!h) return PTB_E_STATE;
-    const int nm = ptbh_node_count(h);
-    std::vector<unsigned char> dfs((size_t)nm * 80), bfs((size_t)nm * 80);
-    std::vector<int> order((size_t)ptbh_index_count(h));
-    ptbh_export(h, dfs.data(), order.data(), 0, 0);
-    ptbh_free(h);
-    // the merged tree is deeper than any single BLAS: keep the two-level walk if it could outgrow the traversal stack
-    // (BVH_STACK_SIZE = 32 entries, two per level, plus the TLAS root that waits underneath)
-    if (2 * ptb_merge::max_depth(dfs.data(), 0) + 3 > PTB_STACK_TOTAL) {
+    // One CWBVH over all of them.  Default: split BVH (spatial splits, host/bvh_build.cpp SpatialBuilder; the reference's second
+    // builder, Src/BVH/Builders/SBVHBuilder.cpp) -- Sponza's long wall / floor triangles overlap everything in a plain SAH tree;
+    // measured with ptbh_trace_stats on bounce rays: 22.8 -> 17.6 node visits and 13.0 -> 8.4 triangle tests per ray for 11 % more
+    // triangle references.  A reference is a (clipped box, triangle) pair: a triangle can sit in several leaves, every leaf entry gets
+    // its own 48-byte record below.  The merged tree is deeper than any single BLAS: if it could outgrow the traversal stack
+    // (BVH_STACK_SIZE = 32 entries, two per level, plus the TLAS root that waits underneath) the plain SAH tree is tried, then the
+    // two-level walk is kept.
+    void* h = nullptr; int nm = 0;
+    std::vector<unsigned char> dfs;
+    std::vector<int> order;
+    for (int attempt = ctx->merge_spatial ? 0 : 1; attempt < 2; attempt++) {
+        h = attempt == 0 ? ptbh_build_triangles_sbvh(pos.data(), n, 3e-4f, 96, 2.0f) : ptbh_build_triangles(pos.data(), n, 8, 4.0f, 1.0f);
+        if (!h) return PTB_E_STATE;
+        nm = ptbh_node_count(h);
+        dfs.assign((size_t)nm * 80, 0); order.assign((size_t)ptbh_index_count(h), 0);
+        ptbh_export(h, dfs.data(), order.data(), 0, 0);
+        ptbh_free(h);
+        if (2 * ptb_merge::max_depth(dfs.data(), 0) + 3 <= PTB_STACK_TOTAL) break;
+        nm = 0;
+    }
+    if (nm == 0) {
         fprintf(stderr, "[ptb] static merge skipped: merged BVH too deep for the %d-entry traversal stack\n", PTB_STACK_TOTAL);
         ctx->merge_slot_root.clear(); ctx->merge_slot_instance.clear();
         upload_roots(ctx, ctx->host_roots);
         return 0;
     }
+    std::vector<unsigned char> bfs((size_t)nm * 80);
+    const int n_refs = (int)order.size();
     // breadth-first re-layout (children of a node stay contiguous and in slot order); child indices become global
     const int base = ctx->node_count;
     ptb_merge::bfs_relayout(dfs.data(), nm, base, bfs.data());
-    std::vector<float4> flat((size_t)n * 3);
-    for (int j = 0; j < n; j++) {
+    std::vector<float4> flat((size_t)n_refs * 3);
+    for (int j = 0; j < n_refs; j++) {
         int src = order[j];
         const float4* r = &ctx->host_tri_pos[(size_t)who[src].x * 3];
         flat[(size_t)j * 3 + 0] = r[0]; flat[(size_t)j * 3 + 1] = r[1];
@@ -655,6 +701,26 @@ static int rebuild_static_merge(ptb_ctx* ctx) {
     CK(cudaMalloc(&ctx->merge_nodes, ((size_t)base + nm) * 80));
     CK(cudaMemcpyAsync(ctx->merge_nodes, ctx->uploaded_nodes, (size_t)base * 80, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ctx->merge_nodes) + (size_t)base * 80, bfs.data(), (size_t)nm * 80, cudaMemcpyHostToDevice, ctx->stream));
+    // Woop maps (double precision on the host): columns (e1, e2, n, p0) of the triangle's frame, inverted; n = e1 x e2
+    std::vector<float4> woop((size_t)n_refs * 3); std::vector<int2> who_ref((size_t)n_refs);
+    for (int j = 0; j < n_refs; j++) {
+        const float4* r = &ctx->host_tri_pos[(size_t)who[order[j]].x * 3];
+        double p0[3] = { r[0].x, r[0].y, r[0].z }, e1[3] = { r[0].w, r[1].x, r[1].y }, e2[3] = { r[1].z, r[1].w, r[2].x };
+        double nn[3] = { e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0] };
+        double det = nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2];          // det [e1 e2 n] = |n|^2
+        double inv = det > 0.0 ? 1.0 / det : 0.0;
+        // rows of [e1 e2 n]^-1: (e2 x n) / det, (n x e1) / det, n / det
+        double r0[3] = { (e2[1] * nn[2] - e2[2] * nn[1]) * inv, (e2[2] * nn[0] - e2[0] * nn[2]) * inv, (e2[0] * nn[1] - e2[1] * nn[0]) * inv };
+        double r1[3] = { (nn[1] * e1[2] - nn[2] * e1[1]) * inv, (nn[2] * e1[0] - nn[0] * e1[2]) * inv, (nn[0] * e1[1] - nn[1] * e1[0]) * inv };
+        double r2[3] = { nn[0] * inv, nn[1] * inv, nn[2] * inv };
+        auto row = [&](const double* m) { return make_float4((float)m[0], (float)m[1], (float)m[2], (float)-(m[0] * p0[0] + m[1] * p0[1] + m[2] * p0[2])); };
+        woop[(size_t)j * 3 + 0] = row(r0); woop[(size_t)j * 3 + 1] = row(r1); woop[(size_t)j * 3 + 2] = row(r2);
+        who_ref[j] = who[order[j]];
+    }
+    CK(cudaMalloc(&ctx->merge_woop, woop.size() * sizeof(float4)));
+    CK(cudaMemcpyAsync(ctx->merge_woop, woop.data(), woop.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMalloc(&ctx->merge_who, who_ref.size() * sizeof(int2)));
+    CK(cudaMemcpyAsync(ctx->merge_who, who_ref.data(), who_ref.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMalloc(&ctx->merge_tris, flat.size() * sizeof(float4)));
     CK(cudaMemcpyAsync(ctx->merge_tris, flat.data(), flat.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMalloc(&ctx->merge_slot_instance_dev, sizeof(int) * slots.size()));
@@ -662,6 +728,7 @@ static int rebuild_static_merge(ptb_ctx* ctx) {
     F.nodes8 = ctx->merge_nodes;
     F.flat_root = base; F.flat_node_count = nm; F.flat_all = (int)slots.size() == M ? 1 : 0;
     F.flat_tris = ctx->merge_tris; F.flat_slot_instance = ctx->merge_slot_instance_dev;
+    F.flat_who = ctx->merge_who; F.flat_woop = ctx->intersector == PTB_INTERSECT_WOOP ? ctx->merge_woop : nullptr;
     upload_roots(ctx, device_roots);
     return upload_pruned_tlas(ctx);
 }
@@ -698,12 +765,51 @@ static int apply_roots(ptb_ctx* ctx, const int32_t* roots, int mesh_count) {
     return upload_pruned_tlas(ctx);
 }
 
-extern "C" int ptb_set_static_merge(ptb_ctx* ctx, int enabled) {
-    if (!ctx) return PTB_E_BADARG;
+extern "C" int ptb_set_static_merge(ptb_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 2) return PTB_E_BADARG;
     CK(cudaSetDevice(ctx->device));
-    if ((enabled != 0) == ctx->merge_enabled) return 0;
-    ctx->merge_enabled = enabled != 0;
+    const bool enabled = mode != 0, spatial = mode != 2;
+    if (enabled == ctx->merge_enabled && (!enabled || spatial == ctx->merge_spatial)) return 0;
+    ctx->merge_enabled = enabled;
+    if (enabled) ctx->merge_spatial = spatial;
     return ctx->has_scene ? rebuild_static_merge(ctx) : 0;
+}
+
+// Pathtracer::resize_free + resize_init (Pathtracer.cpp:255-314): new film size, same scene.  Accumulators, SVGF history and the
+// frame graphs start over; the caller sets the camera for the new film (Camera::resize) and restarts sample_index at 0.
+extern "C" int ptb_resize(ptb_ctx* ctx, int width, int height) {
+    if (!ctx || width <= 0 || height <= 0) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->F.xchg.count > 0) return PTB_E_STATE;           // connected peers hold pointers into the old film: ptb_exchange_disconnect first
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->side_stream) CK(cudaStreamSynchronize(ctx->side_stream));
+    drop_graphs(ctx);
+    if (width == ctx->F.width && height == ctx->F.height) return 0;
+    for (void*& m : ctx->xchg_ipc_opened) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
+    if (ctx->xchg_block) { cudaFree(ctx->xchg_block); ctx->xchg_block = nullptr; }
+    for (void* p : ctx->wave_allocs) cudaFree(p);
+    ctx->wave_allocs.clear();
+    for (void* p : ctx->film_allocs) cudaFree(p);
+    ctx->film_allocs.clear();
+    Frame& F = ctx->F;
+    for (int k = 0; k < PTB_AOV_COUNT; k++) { F.aov[k].fb = nullptr; F.aov[k].acc = nullptr; }
+    F.display = nullptr; ctx->tap_hits = nullptr;
+    { float vp[16], vpp[16]; memcpy(vp, F.svgf.view_projection, 64); memcpy(vpp, F.svgf.view_projection_prev, 64);
+      memset(&F.svgf, 0, sizeof(F.svgf)); memcpy(F.svgf.view_projection, vp, 64); memcpy(F.svgf.view_projection_prev, vpp, 64); }
+    F.width = width; F.height = height;
+    int e = allocate_film(ctx); if (e) return e;
+    ctx->frames_since_reset = 0; ctx->last_sample_index = -1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int ptb_set_intersector(ptb_ctx* ctx, int kind) {
+    if (!ctx || (kind != PTB_INTERSECT_MT && kind != PTB_INTERSECT_WOOP)) return PTB_E_BADARG;
+    if (kind == ctx->intersector) return 0;
+    drop_graphs(ctx);
+    ctx->intersector = kind;
+    ctx->F.flat_woop = (kind == PTB_INTERSECT_WOOP && ctx->F.flat_root >= 0) ? ctx->merge_woop : nullptr;
+    return 0;
 }
 
 extern "C" int ptb_upload_scene(ptb_ctx* ctx, const ptb_scene* s) {

@@ -144,10 +144,34 @@ PTB_DI Hit unpack_hit(uint4 w) {
     return h;
 }
 
+// Woop's test (Woop 2004, "unit triangle"): the ray is mapped by the reference's precomputed affine map, t comes from the z
+// components alone and (u, v) are the mapped hit point.  Opt-in (ptb_set_intersector): north_star names it; the reference itself
+// uses Moeller-Trumbore, and u, v, t differ from it in the last ulps, so this mode is held to the 1e-4 rel-L2 bar, not to bit parity.
+PTB_DI bool woop_test(const Frame& P, int ref, const Ray& ray, float t_max, float& t, float& u, float& v) {
+    const float4* m = P.flat_woop + 3 * size_t(ref);
+    float4 r2 = __ldg(m + 2);
+    float oz = r2.x * ray.o.x + r2.y * ray.o.y + r2.z * ray.o.z + r2.w;
+    float dz = r2.x * ray.d.x + r2.y * ray.d.y + r2.z * ray.d.z;
+    t = -oz / dz;
+    if (!(t > 0.0f && t < t_max)) return false;
+    float4 r0 = __ldg(m), r1 = __ldg(m + 1);
+    u = (r0.x * ray.o.x + r0.y * ray.o.y + r0.z * ray.o.z + r0.w) + t * (r0.x * ray.d.x + r0.y * ray.d.y + r0.z * ray.d.z);
+    v = (r1.x * ray.o.x + r1.y * ray.o.y + r1.z * ray.o.z + r1.w) + t * (r1.x * ray.d.x + r1.y * ray.d.y + r1.z * ray.d.z);
+    return u >= 0.0f && v >= 0.0f && u + v <= 1.0f;
+}
+
 // Moeller-Trumbore, closest hit (Triangle.h:148-174)
 PTB_DI void intersect_triangle(const Frame& P, int mesh_id, int tri_id, const Ray& ray, Hit& hit) {
     float4 c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     const bool flat = mesh_id == PTB_FLAT_MESH;
+    if (flat && P.flat_woop) {
+        float t, u, v;
+        if (woop_test(P, tri_id, ray, hit.t, t, u, v)) {
+            int2 who = __ldg(P.flat_who + tri_id);
+            hit.t = t; hit.u = u; hit.v = v; hit.mesh_id = -(2 + who.y); hit.triangle_id = who.x;
+        }
+        return;
+    }
     TriPos tr = flat ? load_tri_pos_flat(P, tri_id, c) : load_tri_pos(P, tri_id);
     if (flat) { tri_id = __float_as_int(c.y); mesh_id = -(2 + __float_as_int(c.z)); }   // original triangle id; slot resolved when the hit is stored
     float3 h = cross(ray.d, tr.e2);
@@ -167,6 +191,7 @@ PTB_DI void intersect_triangle(const Frame& P, int mesh_id, int tri_id, const Ra
 // any hit (Triangle.h:176-198)
 PTB_DI bool occludes_triangle(const Frame& P, int mesh_id, int tri_id, const Ray& ray, float max_distance) {
     float4 c;
+    if (mesh_id == PTB_FLAT_MESH && P.flat_woop) { float t, u, v; return woop_test(P, tri_id, ray, max_distance, t, u, v); }
     TriPos tr = mesh_id == PTB_FLAT_MESH ? load_tri_pos_flat(P, tri_id, c) : load_tri_pos(P, tri_id);
     float3 h = cross(ray.d, tr.e2);
     float a = dot(tr.e1, h);

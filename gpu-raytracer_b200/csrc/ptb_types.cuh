@@ -197,6 +197,10 @@ struct Frame {
     int           flat_node_count;
     const float4* flat_tris;          // 3 float4 per merged triangle: p0, e1, e2 (36 B) + original triangle id + merged slot
     const int*    flat_slot_instance; // merged slot -> current instance index (TLAS leaf order can change between frames)
+    // Woop intersection (ptb_set_intersector(PTB_INTERSECT_WOOP), merged BVH only): per triangle reference the 3x4 affine map that
+    // takes the triangle to the unit triangle in the z = 0 plane (Woop 2004); ids live in a side table read only on an accepted hit
+    const float4* flat_woop;          // 3 float4 per reference: rows of the map; nullptr = Moeller-Trumbore (what the reference does)
+    const int2*   flat_who;           // (original triangle id, merged slot) per reference
 
     // Ray ordering (see k_bin_count / k_bin_scatter): incoherent queues are traced in direction-bin order through `order`
     int            order_bins;        // 0 = trace in queue order, else 8 (octants) or 64 (8x8 octahedral cells)

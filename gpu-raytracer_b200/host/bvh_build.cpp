@@ -21,6 +21,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <algorithm>
+#include <thread>
 #include <vector>
 #include "static_merge.h"
 
@@ -260,13 +262,14 @@ struct WideConverter {
     struct Choice { Kind kind; int8_t dl, dr; float cost; };
     std::vector<Choice> table; // 7 per BVH2 node: cost of representing the subtree with <= i+1 slots
 
-    WideConverter(const BVH2& i, BVH8& o) : in(i), out(o) {}
+    float c_tri = 1.0f;          // relative cost of one triangle test (the reference's model: 1, BVH8Converter.cpp:24-117)
+    WideConverter(const BVH2& i, BVH8& o, float tri_cost = 1.0f) : in(i), out(o), c_tri(tri_cost) {}
     Choice& at(int node, int i) { return table[size_t(node) * 7 + i]; }
 
     int fill_costs(int ni) {
         const Node2& n = in.nodes[ni];
         if (n.leaf()) {
-            float c = n.box.area() * float(n.count());
+            float c = n.box.area() * float(n.count()) * c_tri;
             for (int i = 0; i < 7; i++) { at(ni, i).kind = LEAF; at(ni, i).cost = c; }
             return int(n.count());
         }
@@ -274,7 +277,7 @@ struct WideConverter {
         int prims = fill_costs(L) + fill_costs(R);
         const float inf = std::numeric_limits<float>::infinity();
         { // whole subtree as ONE slot: either a (<=3 triangle) leaf or an internal node with 8 slots
-            float as_leaf = prims <= 3 ? float(prims) * n.box.area() : inf;
+            float as_leaf = prims <= 3 ? float(prims) * n.box.area() * c_tri : inf;
             float best = inf; int8_t dl = -1, dr = -1;
             for (int k = 0; k < 7; k++) {
                 float c = at(L, k).cost + at(R, 6 - k).cost;
@@ -402,6 +405,285 @@ struct WideConverter {
     }
 };
 
+// ---------------------------------------------------------------- split BVH (spatial splits)
+// SBVH of Stich et al. 2009, the algorithm of the reference's second builder (Src/BVH/Builders/SBVHBuilder.cpp:12-366: full-sweep
+// object split vs. binned spatial split with reference clipping, spatial splits only where the object split's children overlap by
+// more than alpha x the root area, Config.h:58).  Own formulation: recursion over per-node reference vectors (the reference keeps three
+// presorted index arrays), chopped binning over 128 bins, reference unsplitting.  Output: a BVH2 with ONE reference per leaf whose
+// leaf boxes are the (clipped) reference boxes -- the input the CWBVH converter above expects.  A triangle may be referenced by
+// several leaves.  Used for the merged static BVH of libptb (ptb_api.cu: rebuild_static_merge), where fewer node visits and
+// triangle tests per ray are worth a longer one-off build.
+struct Ref { Box box; int tri; };
+
+struct SpatialBuilder {
+    const float* pos;                 // 9 floats per triangle
+    float alpha = 1e-5f;
+    int   bins = 128;
+    float inv_root_area = 0.0f;
+    std::vector<Node2> nodes;
+    std::vector<int>   indices;      // triangle id per leaf, in leaf order
+    size_t max_refs = 0;             // stop splitting spatially once the reference count would exceed this
+
+    static float axis(const V3& v, int d) { return (&v.x)[d]; }
+    static float& axis(V3& v, int d) { return (&v.x)[d]; }
+
+    // bounds of (triangle clipped to the slab lo <= x[d] <= hi), intersected with `within`
+    Box clip_to_slab(int tri, int d, float lo, float hi, const Box& within) const {
+        const float* t = pos + size_t(tri) * 9;
+        V3 v[3] = { { t[0], t[1], t[2] }, { t[3], t[4], t[5] }, { t[6], t[7], t[8] } };
+        Box b = Box::empty();
+        for (int i = 0; i < 3; i++) {
+            const V3& a = v[i]; const V3& c = v[(i + 1) % 3];
+            float pa = axis(a, d), pc = axis(c, d);
+            if (pa >= lo && pa <= hi) b.grow(a);
+            // edge crossings with the two planes
+            for (int k = 0; k < 2; k++) {
+                float plane = k == 0 ? lo : hi;
+                if ((pa < plane && pc > plane) || (pa > plane && pc < plane)) {
+                    float f = (plane - pa) / (pc - pa);
+                    V3 q = { a.x + f * (c.x - a.x), a.y + f * (c.y - a.y), a.z + f * (c.z - a.z) };
+                    axis(q, d) = plane;
+                    b.grow(q);
+                }
+            }
+        }
+        if (b.is_empty()) return b;
+        b.lo = vmax(b.lo, within.lo); b.hi = vmin(b.hi, within.hi);
+        if (b.lo.x > b.hi.x || b.lo.y > b.hi.y || b.lo.z > b.hi.z) return Box::empty();
+        return b;
+    }
+
+    struct ObjSplit { int dim = -1, index = -1; float cost = std::numeric_limits<float>::infinity(); Box left, right; };
+    struct SpaSplit { int dim = -1; float plane = 0.0f, cost = std::numeric_limits<float>::infinity(); int nl = 0, nr = 0; Box left, right; };
+
+    // Object split.  Small nodes: full sweep over the references sorted by box centre (leaves `refs` sorted along the winning axis,
+    // left = the first `index`).  Large nodes: 256 centroid bins per axis (the sweep's O(n log n) sorts would dominate the build);
+    // `refs` is then partitioned so that the left side comes first.
+    ObjSplit object_split(std::vector<Ref>& refs, std::vector<float>& sweep) {
+        const int n = int(refs.size());
+        return n > sweep_limit ? object_split_binned(refs) : object_split_sweep(refs, sweep);
+    }
+    int sweep_limit = 4096;
+
+    ObjSplit object_split_binned(std::vector<Ref>& refs) {
+        ObjSplit best;
+        const int n = int(refs.size()), B = 256;
+        Box cb = Box::empty();
+        for (const Ref& r : refs) cb.grow(r.box.center());
+        std::vector<Box> bin_box(B), right_acc(B); std::vector<int> cnt(B);
+        int best_bin = -1; float best_lo = 0.0f, best_scale = 0.0f;
+        for (int d = 0; d < 3; d++) {
+            float lo = axis(cb.lo, d), extent = axis(cb.hi, d) - lo;
+            if (!(extent > 0.0f)) continue;
+            float scale = float(B) / extent;
+            for (int b = 0; b < B; b++) { bin_box[b] = Box::empty(); cnt[b] = 0; }
+            for (const Ref& r : refs) {
+                int b = int((axis(r.box.center(), d) - lo) * scale); b = b < 0 ? 0 : (b >= B ? B - 1 : b);
+                bin_box[b].grow(r.box); cnt[b]++;
+            }
+            Box acc = Box::empty();
+            for (int b = B - 1; b > 0; b--) { acc.grow(bin_box[b]); right_acc[b] = acc; }
+            Box l = Box::empty(); int nl = 0;
+            for (int b = 1; b < B; b++) {
+                l.grow(bin_box[b - 1]); nl += cnt[b - 1];
+                if (nl == 0 || nl == n) continue;
+                float c = l.area() * float(nl) + right_acc[b].area() * float(n - nl);
+                if (c < best.cost) { best.cost = c; best.dim = d; best.index = nl; best.left = l; best.right = right_acc[b]; best_bin = b; best_lo = lo; best_scale = scale; }
+            }
+        }
+        if (best.dim < 0) {      // all centres coincide: split the list in the middle
+            best.dim = 0; best.index = n / 2; best.left = Box::empty(); best.right = Box::empty();
+            for (int i = 0; i < n; i++) (i < best.index ? best.left : best.right).grow(refs[i].box);
+            best.cost = best.left.area() * float(best.index) + best.right.area() * float(n - best.index);
+            return best;
+        }
+        const int d = best.dim;
+        std::stable_partition(refs.begin(), refs.end(), [&](const Ref& r) {
+            int b = int((axis(r.box.center(), d) - best_lo) * best_scale); b = b < 0 ? 0 : (b >= B ? B - 1 : b);
+            return b < best_bin; });
+        return best;
+    }
+
+    ObjSplit object_split_sweep(std::vector<Ref>& refs, std::vector<float>& sweep) {
+        ObjSplit best;
+        const int n = int(refs.size());
+        std::vector<Ref> sorted_best;
+        for (int d = 0; d < 3; d++) {
+            std::stable_sort(refs.begin(), refs.end(), [d](const Ref& a, const Ref& b) {
+                return axis(a.box.lo, d) + axis(a.box.hi, d) < axis(b.box.lo, d) + axis(b.box.hi, d); });
+            Box l = Box::empty(), r = Box::empty();
+            for (int i = 1; i < n; i++) { l.grow(refs[i - 1].box); sweep[i] = l.area() * float(i); }
+            bool won = false;
+            for (int i = n - 1; i > 0; i--) {
+                r.grow(refs[i].box);
+                float c = sweep[i] + r.area() * float(n - i);
+                if (c < best.cost) { best.cost = c; best.index = i; best.dim = d; best.right = r; won = true; }
+            }
+            if (won && d < 2) sorted_best = refs;
+            if (won && d == 2) sorted_best.clear();
+        }
+        if (!sorted_best.empty()) refs.swap(sorted_best);
+        best.left = Box::empty();
+        for (int i = 0; i < best.index; i++) best.left.grow(refs[i].box);
+        return best;
+    }
+
+    SpaSplit spatial_split(const std::vector<Ref>& refs, const Box& node_box) {
+        SpaSplit best;
+        const int B = bins;
+        std::vector<Box> bin_box(B); std::vector<int> enter(B), leave(B);
+        std::vector<Box> right_acc(B);
+        for (int d = 0; d < 3; d++) {
+            float lo = axis(node_box.lo, d), hi = axis(node_box.hi, d);
+            float extent = hi - lo;
+            if (!(extent > 0.0f)) continue;
+            float scale = float(B) / extent, width = extent / float(B);
+            for (int b = 0; b < B; b++) { bin_box[b] = Box::empty(); enter[b] = leave[b] = 0; }
+            for (const Ref& r : refs) {
+                int b0 = int((axis(r.box.lo, d) - lo) * scale), b1 = int((axis(r.box.hi, d) - lo) * scale);
+                b0 = b0 < 0 ? 0 : (b0 >= B ? B - 1 : b0); b1 = b1 < b0 ? b0 : (b1 >= B ? B - 1 : b1);
+                if (b0 == b1) bin_box[b0].grow(r.box);
+                else for (int b = b0; b <= b1; b++) {
+                    Box c = clip_to_slab(r.tri, d, lo + width * float(b), b == B - 1 ? hi : lo + width * float(b + 1), r.box);
+                    if (!c.is_empty()) bin_box[b].grow(c);
+                }
+                enter[b0]++; leave[b1]++;
+            }
+            Box acc = Box::empty();
+            for (int b = B - 1; b > 0; b--) { acc.grow(bin_box[b]); right_acc[b] = acc; }
+            Box l = Box::empty(); int nl = 0, nr = int(refs.size());
+            for (int b = 1; b < B; b++) {
+                l.grow(bin_box[b - 1]); nl += enter[b - 1]; nr -= leave[b - 1];
+                if (nl == 0 || nr == 0 || l.is_empty() || right_acc[b].is_empty()) continue;
+                float c = l.area() * float(nl) + right_acc[b].area() * float(nr);
+                if (c < best.cost) { best.cost = c; best.dim = d; best.plane = lo + width * float(b); best.nl = nl; best.nr = nr; best.left = l; best.right = right_acc[b]; }
+            }
+        }
+        return best;
+    }
+
+    void make_leaf(int node_index, const Ref& r) {
+        nodes[node_index].box = r.box; nodes[node_index].box.fatten();
+        nodes[node_index].left_or_first = int(indices.size());
+        nodes[node_index].set(1, 0);
+        indices.push_back(r.tri);
+    }
+
+    void build_node(int node_index, std::vector<Ref>& refs, const Box& box, size_t& budget) {
+        const int n = int(refs.size());
+        nodes[node_index].box = box;
+        if (n == 1) { make_leaf(node_index, refs[0]); return; }
+        std::vector<float> sweep(size_t(n) + 1);
+        ObjSplit os = object_split(refs, sweep);
+        std::vector<Ref> left, right;
+        Box lbox, rbox; int dim = os.dim;
+        bool spatial = false;
+        if (n > 2 && budget > 0) {
+            Box ov; ov.lo = vmax(os.left.lo, os.right.lo); ov.hi = vmin(os.left.hi, os.right.hi);
+            bool overlap = ov.lo.x < ov.hi.x && ov.lo.y < ov.hi.y && ov.lo.z < ov.hi.z;
+            if (overlap && ov.area() * inv_root_area > alpha) {
+                SpaSplit ss = spatial_split(refs, box);
+                if (ss.dim >= 0 && ss.cost < os.cost) {
+                    // distribute; straddling references are split unless moving them whole to one side is cheaper (unsplitting)
+                    Box lb = Box::empty(), rb = Box::empty();
+                    std::vector<Ref> straddle;
+                    for (const Ref& r : refs) {
+                        if (axis(r.box.hi, ss.dim) <= ss.plane) { left.push_back(r); lb.grow(r.box); }
+                        else if (axis(r.box.lo, ss.dim) >= ss.plane) { right.push_back(r); rb.grow(r.box); }
+                        else straddle.push_back(r);
+                    }
+                    int nl = int(left.size() + straddle.size()), nr = int(right.size() + straddle.size());
+                    for (const Ref& r : straddle) {
+                        Box cl = clip_to_slab(r.tri, ss.dim, axis(box.lo, ss.dim), ss.plane, r.box);
+                        Box cr = clip_to_slab(r.tri, ss.dim, ss.plane, axis(box.hi, ss.dim), r.box);
+                        if (cl.is_empty() && cr.is_empty()) { cl = r.box; }      // numerically degenerate: keep it whole on the left
+                        if (cl.is_empty()) { right.push_back({ cr, r.tri }); rb.grow(cr); nl--; continue; }
+                        if (cr.is_empty()) { left.push_back({ cl, r.tri }); lb.grow(cl); nr--; continue; }
+                        Box l_split = lb; l_split.grow(cl); Box r_split = rb; r_split.grow(cr);
+                        Box l_whole = lb; l_whole.grow(r.box); Box r_whole = rb; r_whole.grow(r.box);
+                        float c_split = l_split.area() * float(nl) + r_split.area() * float(nr);
+                        float c_left  = l_whole.area() * float(nl) + rb.area() * float(nr - 1);
+                        float c_right = lb.area() * float(nl - 1) + r_whole.area() * float(nr);
+                        if (rb.is_empty()) c_left = std::numeric_limits<float>::infinity();
+                        if (lb.is_empty()) c_right = std::numeric_limits<float>::infinity();
+                        if (c_split <= c_left && c_split <= c_right && budget > 0) {
+                            left.push_back({ cl, r.tri }); right.push_back({ cr, r.tri }); lb = l_split; rb = r_split; budget--;
+                        } else if (c_left <= c_right) { left.push_back(r); lb = l_whole; nr--; }
+                        else { right.push_back(r); rb = r_whole; nl--; }
+                    }
+                    if (!left.empty() && !right.empty() && int(left.size()) < n && int(right.size()) < n) {
+                        spatial = true; lbox = lb; rbox = rb; dim = ss.dim;
+                    } else { left.clear(); right.clear(); }
+                }
+            }
+        }
+        if (!spatial) {
+            left.assign(refs.begin(), refs.begin() + os.index);
+            right.assign(refs.begin() + os.index, refs.end());
+            lbox = os.left; rbox = os.right;
+        }
+        { std::vector<Ref>().swap(refs); }                       // the parent's references are no longer needed
+        int l = int(nodes.size());
+        nodes[node_index].left_or_first = l;
+        nodes[node_index].set(0, uint32_t(dim));
+        nodes.emplace_back(); nodes.emplace_back();
+        if (n >= parallel_limit && left.size() > 1 && right.size() > 1) {
+            // big node: the two subtrees are built concurrently, each into its own arrays, then spliced in
+            SpatialBuilder a = child_builder(), b = child_builder();
+            size_t bl = budget * left.size() / size_t(n), br = budget - bl;
+            std::thread worker([&]() { a.nodes.emplace_back(); a.nodes.emplace_back(); a.build_node(0, left, lbox, bl); });
+            b.nodes.emplace_back(); b.nodes.emplace_back(); b.build_node(0, right, rbox, br);
+            worker.join();
+            budget = bl + br;
+            splice(l, a); splice(l + 1, b);
+        } else {
+            build_node(l, left, lbox, budget);
+            build_node(l + 1, right, rbox, budget);
+        }
+    }
+
+    int parallel_limit = 16384;
+    SpatialBuilder child_builder() const {
+        SpatialBuilder c; c.pos = pos; c.alpha = alpha; c.bins = bins; c.inv_root_area = inv_root_area; c.sweep_limit = sweep_limit; c.parallel_limit = parallel_limit;
+        return c;
+    }
+    // sub-builder `c` holds a subtree with its root in slot 0 (slot 1 unused): root -> our slot `at`, the rest appended
+    void splice(int at, const SpatialBuilder& c) {
+        const int node_base = int(nodes.size()) - 2, index_base = int(indices.size());
+        auto fix = [&](Node2 nd) { if (nd.leaf()) nd.left_or_first += index_base; else nd.left_or_first += node_base; return nd; };
+        nodes[at] = fix(c.nodes[0]);
+        for (size_t k = 2; k < c.nodes.size(); k++) nodes.push_back(fix(c.nodes[k]));
+        indices.insert(indices.end(), c.indices.begin(), c.indices.end());
+    }
+
+    void build(int n) {
+        std::vector<Ref> refs; refs.resize(size_t(n));
+        Box root = Box::empty();
+        for (int i = 0; i < n; i++) {
+            const float* t = pos + size_t(i) * 9;
+            Box b = Box::empty(); b.grow(V3{ t[0], t[1], t[2] }); b.grow(V3{ t[3], t[4], t[5] }); b.grow(V3{ t[6], t[7], t[8] });
+            refs[i] = { b, i }; root.grow(b);
+        }
+        inv_root_area = 1.0f / root.area();
+        nodes.clear(); indices.clear();
+        nodes.reserve(size_t(4) * n + 2); indices.reserve(size_t(2) * n);
+        nodes.emplace_back(); nodes.emplace_back();
+        size_t budget = max_refs > size_t(n) ? max_refs - size_t(n) : 0;
+        build_node(0, refs, root, budget);
+        refit(0);
+    }
+
+    // leaf boxes were widened where flat (Box::fatten, like the plain builder's primitive boxes): make every inner box the union of
+    // its children again, so that a child never sticks out of the box its quantisation grid is laid over
+    Box refit(int ni) {
+        if (nodes[ni].leaf()) return nodes[ni].box;
+        int l = nodes[ni].left_or_first;
+        Box b = refit(l); b.grow(refit(l + 1));
+        nodes[ni].box = b;
+        return b;
+    }
+};
+
 struct Built {
     BVH2 bvh2;
     BVH8 bvh8;
@@ -457,6 +739,104 @@ void* ptbh_build_boxes(const float* aabb, int n, int kind) {
         p.center[i] = p.box[i].center();
     }
     return finish(p, kind, 0.0f, 0.0f);
+}
+
+
+// Split-BVH build (spatial splits) -> CWBVH.  alpha: minimum overlap of the object split's children, relative to the root's area,
+// for a spatial split to be tried (the reference's --sbvh-alpha, Config.h:58); max_dup: cap on references as a multiple of n
+// (e.g. 1.5).  ptbh_index_count() is the number of REFERENCES (>= n): indices may repeat a triangle.
+static float g_tri_cost = 1.0f;
+void ptbh_set_tri_cost(float c) { g_tri_cost = c; }     // tuning knob for tools/cpu_bvh_quality.py
+void* ptbh_build_triangles_sbvh(const float* pos, int n, float alpha, int bins, float max_dup) {
+    if (n <= 0) return nullptr;
+    SpatialBuilder sb; sb.pos = pos; sb.alpha = alpha; sb.bins = bins < 8 ? 8 : bins;
+    sb.max_refs = size_t(double(n) * double(max_dup < 1.0f ? 1.0f : max_dup));
+    sb.build(n);
+    Built* b = new Built(); b->kind = 8;
+    BVH2 raw; raw.nodes.swap(sb.nodes); raw.indices.swap(sb.indices);
+    WideConverter(raw, b->bvh8, g_tri_cost).run();
+    return b;
+}
+
+// CPU closest-hit walk of a built CWBVH (tuning / test aid: visit counts per ray predict the device kernel's work; BVH8.h:113-274
+// semantics: octant-ordered child pops, triangles of a node tested before descending, culling against the current closest hit).
+// rays: n x 6 floats (origin, direction).  Adds the visits to counts[0] (nodes) and counts[1] (triangle tests); hit_t / hit_tri may be null.
+void ptbh_trace_stats(void* h, const float* pos, const float* rays, int n_rays, unsigned long long* counts, float* hit_t, int* hit_tri) {
+    Built* b = static_cast<Built*>(h);
+    const std::vector<Node8>& nodes = b->bvh8.nodes; const std::vector<int>& idx = b->bvh8.indices;
+    unsigned long long n_nodes = 0, n_tris = 0;
+    struct Entry { uint32_t base, mask; };
+    for (int r = 0; r < n_rays; r++) {
+        const float* ray = rays + size_t(r) * 6;
+        float ox = ray[0], oy = ray[1], oz = ray[2], dx = ray[3], dy = ray[4], dz = ray[5];
+        unsigned oct = (dx < 0.0f ? 0u : 4u) | (dy < 0.0f ? 0u : 2u) | (dz < 0.0f ? 0u : 1u);   // "inverse octant", BVH8.h:5-10
+        float best = std::numeric_limits<float>::infinity(); int best_tri = -1;
+        Entry stack[64]; int sp = 0;
+        Entry cur = { 0u, 0x80000000u };      // root: pseudo group with one child bit
+        for (;;) {
+            uint32_t tri_base = 0, tri_mask = 0;
+            if (cur.mask & 0xff000000u) {
+                int bit = 31 - __builtin_clz(cur.mask);
+                uint32_t imask_hits = cur.mask;
+                cur.mask &= ~(1u << bit);
+                if (cur.mask & 0xff000000u) stack[sp++] = cur;
+                unsigned slot = unsigned(bit - 24) ^ oct;
+                unsigned rel = unsigned(__builtin_popcount(imask_hits & ~(0xffffffffu << slot)));
+                const Node8& nd = nodes[cur.base + rel];
+                n_nodes++;
+                float ex, ey, ez; uint32_t u;
+                u = uint32_t(nd.e[0]) << 23; std::memcpy(&ex, &u, 4); u = uint32_t(nd.e[1]) << 23; std::memcpy(&ey, &u, 4); u = uint32_t(nd.e[2]) << 23; std::memcpy(&ez, &u, 4);
+                float aix = ex / dx, aiy = ey / dy, aiz = ez / dz;
+                float aox = (nd.p.x - ox) / dx, aoy = (nd.p.y - oy) / dy, aoz = (nd.p.z - oz) / dz;
+                uint32_t hm = 0;
+                for (int j = 0; j < 8; j++) {
+                    uint8_t meta = nd.meta[j];
+                    if (!meta) continue;
+                    float lx = float(dx < 0.0f ? nd.qhi_x[j] : nd.qlo_x[j]), hx = float(dx < 0.0f ? nd.qlo_x[j] : nd.qhi_x[j]);
+                    float ly = float(dy < 0.0f ? nd.qhi_y[j] : nd.qlo_y[j]), hy = float(dy < 0.0f ? nd.qlo_y[j] : nd.qhi_y[j]);
+                    float lz = float(dz < 0.0f ? nd.qhi_z[j] : nd.qlo_z[j]), hz = float(dz < 0.0f ? nd.qlo_z[j] : nd.qhi_z[j]);
+                    float tmin = std::fmax(std::fmax(lx * aix + aox, ly * aiy + aoy), std::fmax(lz * aiz + aoz, 0.0f));
+                    float tmax = std::fmin(std::fmin(hx * aix + aox, hy * aiy + aoy), std::fmin(hz * aiz + aoz, best));
+                    if (tmin < tmax) {
+                        bool inner = (meta & 0x18) == 0x18 && (meta & 0x20);     // 001xxxxx with index >= 24
+                        if (nd.imask & (1u << j)) hm |= 1u << (24 + ((unsigned(meta) & 7u) ^ oct));
+                        else hm |= (uint32_t(meta) >> 5) << (meta & 31u);
+                        (void)inner;
+                    }
+                }
+                cur.base = nd.base_child; cur.mask = (hm & 0xff000000u) | nd.imask;
+                tri_base = nd.base_triangle; tri_mask = hm & 0x00ffffffu;
+            } else {
+                tri_base = cur.base; tri_mask = cur.mask; cur = { 0u, 0u };
+            }
+            while (tri_mask) {
+                int tb = 31 - __builtin_clz(tri_mask); tri_mask &= ~(1u << tb);
+                int ti = idx[tri_base + unsigned(tb)];
+                n_tris++;
+                const float* t = pos + size_t(ti) * 9;
+                float e1x = t[3] - t[0], e1y = t[4] - t[1], e1z = t[5] - t[2], e2x = t[6] - t[0], e2y = t[7] - t[1], e2z = t[8] - t[2];
+                float hx = dy * e2z - dz * e2y, hy = dz * e2x - dx * e2z, hz = dx * e2y - dy * e2x;
+                float a = e1x * hx + e1y * hy + e1z * hz, f = 1.0f / a;
+                float sx = ox - t[0], sy = oy - t[1], sz = oz - t[2];
+                float uu = f * (sx * hx + sy * hy + sz * hz);
+                if (uu >= 0.0f && uu <= 1.0f) {
+                    float qx = sy * e1z - sz * e1y, qy = sz * e1x - sx * e1z, qz = sx * e1y - sy * e1x;
+                    float vv = f * (dx * qx + dy * qy + dz * qz);
+                    if (vv >= 0.0f && uu + vv <= 1.0f) {
+                        float tt = f * (e2x * qx + e2y * qy + e2z * qz);
+                        if (tt > 0.0f && tt < best) { best = tt; best_tri = ti; }
+                    }
+                }
+            }
+            if ((cur.mask & 0xff000000u) == 0) {
+                if (sp == 0) break;
+                cur = stack[--sp];
+            }
+        }
+        if (hit_t) hit_t[r] = best;
+        if (hit_tri) hit_tri[r] = best_tri;
+    }
+    counts[0] += n_nodes; counts[1] += n_tris;
 }
 
 int ptbh_kind(void* h)        { return static_cast<Built*>(h)->kind; }

@@ -68,7 +68,7 @@ class PtbTraversalStats(ctypes.Structure):
 
 
 # every symbol include/ptb.h declares (tests check the built library exports exactly these)
-ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_reserve_wave", "ptb_set_ray_ordering", "ptb_set_static_merge", "ptb_render_frame",
+ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_reserve_wave", "ptb_set_ray_ordering", "ptb_set_static_merge", "ptb_set_intersector", "ptb_resize", "ptb_render_frame",
                "ptb_measure_traversal", "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_download", "ptb_get_ray_stats", "ptb_set_pixel_query", "ptb_get_pixel_query", "ptb_get_stream", "ptb_export_rows",
                "ptb_assemble_rows", "ptb_exchange_create", "ptb_exchange_connect", "ptb_exchange_connect_ipc", "ptb_exchange_frame", "ptb_exchange_disconnect", "ptb_debug_read", "ptb_launch_count", "ptb_set_timing", "ptb_get_stage_ms", "ptb_stage_name",
                "ptb_error_string"]
@@ -94,6 +94,8 @@ def lib():
         l.ptb_reserve_wave.argtypes = [vp, ci]
         l.ptb_set_ray_ordering.argtypes = [vp, ci]
         l.ptb_set_static_merge.argtypes = [vp, ci]
+        l.ptb_set_intersector.argtypes = [vp, ci]
+        l.ptb_resize.argtypes = [vp, ci, ci]
         l.ptb_measure_traversal.argtypes = [vp, ci, ctypes.POINTER(PtbTraversalStats)]
         l.ptb_sync.argtypes = [vp]
         l.ptb_get_aov.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(ci)]
@@ -331,7 +333,23 @@ class Pathtracer:
 
     def set_static_merge(self, enabled):
         """include/ptb.h: ptb_set_static_merge (identity-transform instances traced through one merged CWBVH)."""
-        _check(lib().ptb_set_static_merge(self._ctx, int(bool(enabled))), "ptb_set_static_merge")
+        _check(lib().ptb_set_static_merge(self._ctx, int(enabled)), "ptb_set_static_merge")     # False/0 off, True/1 SBVH, 2 plain SAH
+
+    def resize(self, blob):
+        """Pathtracer::resize_free + resize_init (Pathtracer.cpp:255-314): same scene, the film size and camera block of `blob`
+        (scene.retarget_blob); accumulation restarts."""
+        w, h = int(blob["width"]), int(blob["height"])
+        _check(lib().ptb_resize(self._ctx, w, h), "ptb_resize")
+        self.screen_width, self.screen_height, self.screen_pitch = w, h, (w + 31) // 32 * 32
+        self._camera = camera_struct(blob["camera"])
+        self._view_projection = np.ascontiguousarray(blob["view_projection"], dtype=np.float32)
+        self._view_projection_prev = self._view_projection.copy()
+        self.invalidated_camera = True; self.invalidated_gpu_config = True
+        self.sample_index = 0
+
+    def set_intersector(self, kind):
+        """include/ptb.h: ptb_set_intersector -- "mt" (reference's Moeller-Trumbore, default) or "woop" (merged BVH only)."""
+        _check(lib().ptb_set_intersector(self._ctx, {"mt": 0, "woop": 1}[kind] if isinstance(kind, str) else int(kind)), "ptb_set_intersector")
 
     def exchange_create(self):
         """Allocates this rank's exchange block; returns (device base pointer, 64-byte CUDA IPC handle)."""

@@ -58,6 +58,10 @@ def hostlib():
         lib.ptbh_export.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         lib.ptbh_free.restype = None
         lib.ptbh_free.argtypes = [ctypes.c_void_p]
+        lib.ptbh_build_triangles_sbvh.restype = ctypes.c_void_p
+        lib.ptbh_build_triangles_sbvh.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_float]
+        lib.ptbh_trace_stats.restype = None
+        lib.ptbh_trace_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _hostlib = lib
     return _hostlib
 
@@ -91,6 +95,23 @@ class BuiltBVH:
 def build_blas(positions: np.ndarray, kind: int, sah_node=4.0, sah_leaf=1.0) -> BuiltBVH:
     pos = np.ascontiguousarray(positions, dtype=f32).reshape(-1, 9)
     return BuiltBVH(hostlib().ptbh_build_triangles(pos.ctypes.data, pos.shape[0], kind, sah_node, sah_leaf))
+
+
+def build_blas_sbvh(positions: np.ndarray, alpha=3e-4, bins=96, max_dup=2.0) -> BuiltBVH:
+    """CWBVH over a split BVH (spatial splits; host/bvh_build.cpp SpatialBuilder).  index_count >= triangle count: a triangle may be
+    referenced by several leaves.  This is what libptb builds for the merged static BVH."""
+    pos = np.ascontiguousarray(positions, dtype=f32).reshape(-1, 9)
+    return BuiltBVH(hostlib().ptbh_build_triangles_sbvh(pos.ctypes.data, pos.shape[0], alpha, bins, max_dup))
+
+
+def trace_stats(bvh: BuiltBVH, positions: np.ndarray, rays: np.ndarray):
+    """CPU closest-hit walk of a CWBVH (ptbh_trace_stats): (nodes per ray, triangle tests per ray, t[n], triangle id[n])."""
+    pos = np.ascontiguousarray(positions, dtype=f32).reshape(-1, 9)
+    r = np.ascontiguousarray(rays, dtype=f32).reshape(-1, 6)
+    counts = (ctypes.c_ulonglong * 2)(0, 0)
+    t = np.empty(r.shape[0], dtype=f32); tri = np.empty(r.shape[0], dtype=np.int32)
+    hostlib().ptbh_trace_stats(bvh.h, pos.ctypes.data, r.ctypes.data, r.shape[0], counts, t.ctypes.data, tri.ctypes.data)
+    return counts[0] / r.shape[0], counts[1] / r.shape[0], t, tri
 
 
 def build_tlas(aabbs: np.ndarray, kind: int) -> BuiltBVH:
@@ -785,6 +806,38 @@ def save_blob(blob, path):
     arrays["meta_json"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     np.savez_compressed(path, **arrays)      # the staged blobs travel to the GPU box with every gpurun call
+
+
+def dump_raw(blob, path, camera_only=False):
+    """Flat binary dump for non-Python hosts (tests/cpp/facade_render.cpp reads it): magic, entry count, then per entry a
+    32-byte name, an int64 byte count and the bytes."""
+    import struct
+    items = []
+    def put(name, arr):
+        a = np.ascontiguousarray(arr)
+        items.append((name, a.tobytes()))
+    put("camera", np.asarray(blob["camera"], dtype=f32)); put("view_projection", np.asarray(blob["view_projection"], dtype=f32))
+    put("width", np.int32(blob["width"])); put("height", np.int32(blob["height"]))
+    if not camera_only:
+        for k in ("triangles", "bvh_nodes", "mesh_bvh_root_indices", "mesh_material_ids", "mesh_transforms", "mesh_transforms_inv", "mesh_transforms_prev",
+                  "material_types", "materials", "media", "pmj", "blue_noise", "light_triangle_indices", "light_triangle_cdf", "light_mesh_cdf",
+                  "light_mesh_triangle_span", "light_mesh_transform_indices"):
+            put(k, blob[k])
+        sky = np.ascontiguousarray(blob["sky"], dtype=f32)
+        put("sky", sky); put("sky_height", np.int32(sky.shape[0])); put("sky_width", np.int32(sky.shape[1])); put("sky_scale", f32(blob["sky_scale"]))
+        put("bvh_kind", np.int32(blob["bvh_kind"])); put("tlas_node_count", np.int32(blob["tlas_node_count"])); put("num_bounces", np.int32(blob["num_bounces"]))
+        put("lights_total_weight", f32(blob["lights_total_weight"]))
+        put("texture_count", np.int32(len(blob["textures"])))
+        for i, t in enumerate(blob["textures"]):
+            meta = np.array([1 if t["format"] == "bc1" else 0, t["width"], t["height"], len(t["levels"]), 0], dtype=np.int32)
+            meta[4:5].view(f32)[0] = t["lod_bias"]
+            put(f"tex{i}_meta", meta)
+            for l, lv in enumerate(t["levels"]):
+                put(f"tex{i}_l{l}", np.asarray(lv, dtype=np.uint8))
+    with open(path, "wb") as f:
+        f.write(b"PTBRAW1\0"); f.write(struct.pack("<i", len(items)))
+        for name, data in items:
+            f.write(name.encode().ljust(32, b"\0")[:32]); f.write(struct.pack("<q", len(data))); f.write(data)
 
 
 def load_blob(path):

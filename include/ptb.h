@@ -174,8 +174,22 @@ int  ptb_export_rows(ptb_ctx* ctx, int aov_type, void* device_dst, int* owned_ro
 int  ptb_assemble_rows(ptb_ctx* ctx, const void* device_src, int max_rows, void* device_dst);
 /* Static merge (default on): instances with an identity transform (root bit 31) are additionally built into ONE CWBVH at
  * upload (CPU SAH build inside ptb_upload_scene / ptb_update_instances) and traced through it instead of TLAS -> BLAS
- * (BVH8.h:204-232); hits still report the original (mesh_id, triangle_id).  0 = trace the reference's two-level hierarchy only. */
-int  ptb_set_static_merge(ptb_ctx* ctx, int enabled);
+ * (BVH8.h:204-232); hits still report the original (mesh_id, triangle_id).  mode 0 = trace the reference's two-level hierarchy only
+ * (every pixel bit-identical to the reference kernels); 1 = merged tree built with spatial splits (the algorithm of the reference's
+ * SBVH builder, Src/BVH/Builders/SBVHBuilder.cpp; default); 2 = merged tree built with the plain full-sweep SAH builder. */
+int  ptb_set_static_merge(ptb_ctx* ctx, int mode);
+/* Ray-triangle test used inside the merged static BVH.  PTB_INTERSECT_MT (default) = Moeller-Trumbore, the reference's test
+ * (Src/CUDA/Raytracing/Triangle.h:148-198), bit-exact.  PTB_INTERSECT_WOOP = Woop's precomputed unit-triangle map (one 48-byte affine
+ * map per triangle reference, built at upload): u, v, t differ from the reference in the last ulps, so frames agree within the
+ * 1e-4 rel-L2 bar instead of bit for bit (tests/test_gpu_configs.py reports the hit-id mismatch rate).  Instances outside the
+ * merged tree (moving / transformed ones) keep Moeller-Trumbore. */
+/* Pathtracer::resize_free + resize_init (Src/Renderer/Integrators/Pathtracer.cpp:255-314): new film size for the same scene.
+ * Accumulators, SVGF / TAA history and cached frame graphs start over; set the camera for the new film afterwards (Camera::resize)
+ * and restart sample_index at 0.  Not allowed while a frame exchange is connected (PTB_E_STATE). */
+int  ptb_resize(ptb_ctx* ctx, int width, int height);
+#define PTB_INTERSECT_MT   0
+#define PTB_INTERSECT_WOOP 1
+int  ptb_set_intersector(ptb_ctx* ctx, int kind);
 /* Trace order of secondary and shadow rays: 0 = queue (emission) order like the reference's kernel_trace_* (Pathtracer.cu:165-197),
  * 8 / 64 = counting-sorted by direction bin (octants / 8x8 octahedral cells) before each trace launch.  A scheduling choice
  * only: every pixel gets the same rays and the same result, bit for bit. */

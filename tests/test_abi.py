@@ -69,3 +69,13 @@ def test_no_texture_waterfall_clobber_in_sass():
     through warp-uniform handles; this guards against a recompile re-introducing the pattern."""
     import sass_scan
     assert sass_scan.scan(build.build_cuda()) == []
+
+
+def test_cpp_facade_builds_and_exports_the_reference_entry_points():
+    """host/ptb_pathtracer.{h,cpp}: the compiled C++ facade carries the reference's Integrator / Pathtracer entry points."""
+    import subprocess
+    from gpu_raytracer_b200 import build
+    so = build.build_facade()
+    sym = subprocess.run(["nm", "-DC", so], capture_output=True, text=True).stdout
+    for name in ("cuda_init", "cuda_free", "resize_init", "resize_free", "update", "render", "set_pixel_query"):
+        assert f"ptb::Pathtracer::{name}(" in sym, name

@@ -199,3 +199,52 @@ def test_static_merge_depth_bound():
         return 1 + max([walk(base + k) for k in range(kids)], default=0)
     d = lib.ptbh_max_depth(nd.ctypes.data, 0)
     assert d == walk(0) and 3 <= d and 2 * d + 3 <= 32
+
+
+# ---------------------------------------------------------------------------------------------- split BVH (merged static tree)
+def _long_triangles(n, seed):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-2, 2, size=(n, 1, 3))
+    tri = c + (rng.random((n, 3, 3)) - 0.5) * np.array([1.6, 0.08, 0.5])      # long, thin, heavily overlapping boxes: the SBVH case
+    flat = rng.integers(0, n, size=n // 8)
+    tri[flat, :, 1] = tri[flat, :1, 1]                                            # axis-aligned flat ones (zero-thickness boxes)
+    return np.ascontiguousarray(tri, dtype=np.float32)
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (40, 2), (3000, 3)])
+def test_sbvh_finds_the_same_closest_hits_as_the_sah_tree(n, seed):
+    """Spatial splits duplicate references and clip their boxes; the closest hit of every ray must stay what the plain SAH tree
+    (verified against brute force above) finds -- same t bits, same triangle -- and every triangle must be referenced."""
+    tri = _long_triangles(n, seed)
+    rng = np.random.default_rng(seed + 10)
+    o = rng.uniform(-3, 3, size=(4000, 3)); d = rng.normal(size=(4000, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    sah = scene.build_blas(tri, 8); sb = scene.build_blas_sbvh(tri, alpha=1e-5, bins=32)
+    _, idx = sb.export()
+    assert set(idx.tolist()) == set(range(n)) and sb.index_count >= n
+    a = scene.trace_stats(sah, tri, rays); b = scene.trace_stats(sb, tri, rays)
+    assert np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
+    hit = np.isfinite(a[2])
+    assert not hit.any() or (a[3][hit] != b[3][hit]).mean() < 2e-3
+    if n >= 3000:
+        assert hit.mean() > 0.2
+        assert b[0] < a[0] and b[1] < a[1]                                        # and it is the better tree for this geometry
+        assert sb.index_count > n                                                 # ... because it actually split something
+
+
+def test_sbvh_children_stay_inside_their_parents():
+    """Flat leaves are widened (Box::fatten); the refit keeps every child box inside the box its quantisation grid spans --
+    a child sticking out would wrap around in the 8-bit grid."""
+    tri = _long_triangles(500, 5)
+    sb = scene.build_blas_sbvh(tri, alpha=1e-6, bins=32)
+    nodes, idx = sb.export()
+    p, e, imask, base_child, base_tri, meta, q = decode_nodes8(nodes)
+    for ni in range(sb.node_count):
+        for slot in range(8):
+            if meta[ni, slot] == 0:
+                continue
+            assert (q[ni, 0::2, slot] <= q[ni, 1::2, slot]).all()                # lo <= hi on every axis
+    # every referenced triangle lies inside the dequantised box of the leaf slot that references it (clipped to that box's slab)
+    rays = np.concatenate([tri.mean(1) + np.array([0, 0, 5.0]), np.tile([0, 0, -1.0], (len(tri), 1))], 1).astype(np.float32)
+    _, _, t, hit_tri = scene.trace_stats(sb, tri, rays)
+    assert np.isfinite(t).all()                                                   # a ray through each centroid hits something

