@@ -247,4 +247,5 @@ def test_sbvh_children_stay_inside_their_parents():
     # every referenced triangle lies inside the dequantised box of the leaf slot that references it (clipped to that box's slab)
     rays = np.concatenate([tri.mean(1) + np.array([0, 0, 5.0]), np.tile([0, 0, -1.0], (len(tri), 1))], 1).astype(np.float32)
     _, _, t, hit_tri = scene.trace_stats(sb, tri, rays)
-    assert np.isfinite(t).all()                                                   # a ray through each centroid hits something
+    _, _, t_ref, _ = scene.trace_stats(scene.build_blas(tri, 8), tri, rays)
+    assert np.array_equal(t.view(np.uint32), t_ref.view(np.uint32)) and np.isfinite(t).mean() > 0.9     # a ray through each centroid
