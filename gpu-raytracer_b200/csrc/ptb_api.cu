@@ -90,7 +90,8 @@ struct ptb_ctx {
     int last_sample_index = -1;
     int frames_since_reset = 0;
     std::string last_error;
-    float4* svgf_ping[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };
+    SVGFHistory local_hist[2] = {};                   // SVGF / TAA temporal state of a single-GPU context (two parities)
+    unsigned svgf_frames = 0;                         // filtered frames so far: frame k writes parity k & 1
     int pixel_query_host[3] = { -1, -1, -1 };
     // shadow rays of bounce b and extension rays of bounce b+1 are independent until the next sort: the shadow trace runs on a
     // side stream so that the tail of one persistent trace kernel is filled by the CTAs of the other (render_wave)
@@ -268,8 +269,8 @@ static void preload_kernels() {
     preload(k_shade<BSDFDiffuse>); preload(k_shade<BSDFPlastic>); preload(k_shade<BSDFDielectric>); preload(k_shade<BSDFConductor>);
     preload(k_bin_count<false>); preload(k_bin_count<true>); preload(k_bin_scatter<false>); preload(k_bin_scatter<true>);
     preload(k_tap_primary_hits); preload(k_export_rows); preload(k_assemble_rows);
-    preload(k_exchange_wait); preload(k_svgf_wait_consumed); preload(k_svgf_push); preload(k_svgf_wait_arrivals); preload(k_svgf_signal_consumed);
-    preload(k_svgf_reproject); preload(k_svgf_variance); preload(k_svgf_atrous); preload(k_svgf_finalize); preload(k_taa); preload(k_taa_finalize);
+    preload(k_exchange_wait); preload(k_svgf_push); preload(k_svgf_wait_arrivals); preload(k_svgf_push_display);
+    preload(k_svgf_reproject); preload(k_svgf_variance); preload(k_svgf_atrous<0>); preload(k_svgf_atrous<1>); preload(k_svgf_atrous<2>); preload(k_svgf_finalize); preload(k_taa); preload(k_taa_finalize);
     preload(k_clear_framebuffers); preload(k_apply_uploads);
     preload(k_integrate_dielectric); preload(k_average_dielectric); preload(k_integrate_conductor); preload(k_average_conductor); preload(k_dump_luts);
     cudaGetLastError();
@@ -373,26 +374,28 @@ static int ensure_aov(ptb_ctx* ctx, int k) {
 
 static int ensure_svgf(ptb_ctx* ctx) {
     Frame& F = ctx->F;
-    if (F.svgf.history_length) return 0;
+    if (F.svgf.moment) return 0;
     const size_t pixels = (size_t)F.pitch * F.height;
     int e = 0;
     e |= film_alloc(ctx, &F.svgf.gbuf_normal_depth, pixels); e |= film_alloc(ctx, &F.svgf.gbuf_ids, pixels); e |= film_alloc(ctx, &F.svgf.gbuf_screen_prev, pixels);
-    e |= film_alloc(ctx, &F.svgf.moment, pixels); e |= film_alloc(ctx, &F.svgf.history_length, pixels);
-    e |= film_alloc(ctx, &F.svgf.history_direct, pixels); e |= film_alloc(ctx, &F.svgf.history_indirect, pixels);
-    e |= film_alloc(ctx, &F.svgf.history_moment, pixels); e |= film_alloc(ctx, &F.svgf.history_normal_depth, pixels);
-    e |= film_alloc(ctx, &F.svgf.taa_prev, pixels); e |= film_alloc(ctx, &F.svgf.taa_curr, pixels);
+    e |= film_alloc(ctx, &F.svgf.moment, pixels); e |= film_alloc(ctx, &F.svgf.taa_curr, pixels);
     if (e) return PTB_E_STATE;
     CK(cudaMemsetAsync(F.svgf.gbuf_normal_depth, 0, pixels * sizeof(float4), ctx->stream));
     CK(cudaMemsetAsync(F.svgf.gbuf_ids, 0, pixels * sizeof(int2), ctx->stream));
     CK(cudaMemsetAsync(F.svgf.gbuf_screen_prev, 0, pixels * sizeof(float2), ctx->stream));
     CK(cudaMemsetAsync(F.svgf.moment, 0, pixels * sizeof(float4), ctx->stream));
-    CK(cudaMemsetAsync(F.svgf.history_length, 0, pixels * sizeof(int), ctx->stream));
-    CK(cudaMemsetAsync(F.svgf.history_direct, 0, pixels * sizeof(float4), ctx->stream));
-    CK(cudaMemsetAsync(F.svgf.history_indirect, 0, pixels * sizeof(float4), ctx->stream));
-    CK(cudaMemsetAsync(F.svgf.history_moment, 0, pixels * sizeof(float4), ctx->stream));
-    CK(cudaMemsetAsync(F.svgf.history_normal_depth, 0, pixels * sizeof(float4), ctx->stream));
-    CK(cudaMemsetAsync(F.svgf.taa_prev, 0, pixels * sizeof(float4), ctx->stream));
     CK(cudaMemsetAsync(F.svgf.taa_curr, 0, pixels * sizeof(float4), ctx->stream));
+    // temporal state, two parities (one GPU; with several GPUs it lives in the exchange block, see render_wave)
+    for (int p = 0; p < 2; p++) {
+        SVGFHistory& h = ctx->local_hist[p];
+        e |= film_alloc(ctx, &h.direct, pixels); e |= film_alloc(ctx, &h.indirect, pixels); e |= film_alloc(ctx, &h.moment, pixels);
+        e |= film_alloc(ctx, &h.normal_depth, pixels); e |= film_alloc(ctx, &h.taa, pixels); e |= film_alloc(ctx, &h.length, pixels);
+        if (e) return PTB_E_STATE;
+        float4* planes[5] = { h.direct, h.indirect, h.moment, h.normal_depth, h.taa };
+        for (float4* q : planes) CK(cudaMemsetAsync(q, 0, pixels * sizeof(float4), ctx->stream));
+        CK(cudaMemsetAsync(h.length, 0, pixels * sizeof(int), ctx->stream));
+    }
+    ctx->svgf_frames = 0;
     return 0;
 }
 
@@ -941,14 +944,33 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
     F.first_sample = first_sample; F.wave_samples = samples;
     F.xchg.push = push && F.xchg.count > 0 && !F.config.enable_svgf;
     F.xchg.svgf = F.xchg.count > 0 && F.config.enable_svgf;
-    if (F.xchg.svgf) {      // the filter's noisy inputs are produced straight into this rank's exchange block
-        float4* base = F.xchg.frames[F.rank];
-        F.aov[PTB_AOV_RADIANCE_DIRECT].fb   = base + xchg_svgf_plane_offset(F.fb_stride, 0);
-        F.aov[PTB_AOV_RADIANCE_INDIRECT].fb = base + xchg_svgf_plane_offset(F.fb_stride, 1);
-        F.aov[PTB_AOV_ALBEDO].fb            = base + xchg_svgf_plane_offset(F.fb_stride, 2);
-        F.svgf.gbuf_normal_depth            = base + xchg_svgf_plane_offset(F.fb_stride, 3);
-        F.svgf.gbuf_ids                     = reinterpret_cast<int2*>(base + xchg_svgf_plane_offset(F.fb_stride, 4));
-        F.svgf.gbuf_screen_prev             = reinterpret_cast<float2*>(base + xchg_svgf_plane_offset(F.fb_stride, 5));
+    if (F.config.enable_svgf) {
+        SVGFBuffers& V = F.svgf;
+        V.parity = int(ctx->svgf_frames & 1u);
+        if (F.xchg.svgf) {
+            // tile-local filter: this rank filters one block of rows; its inputs (stored by the tracing ranks) and the history it owns
+            // live in its exchange block, where the neighbours can reach them
+            const int S = F.fb_stride;
+            F.xchg.rows_per_block = (F.height + F.world - 1) / F.world;
+            V.block_y0 = F.rank * F.xchg.rows_per_block < F.height ? F.rank * F.xchg.rows_per_block : F.height;
+            V.block_y1 = F.rank == F.world - 1 ? F.height : ((F.rank + 1) * F.xchg.rows_per_block < F.height ? (F.rank + 1) * F.xchg.rows_per_block : F.height);
+            V.ext_y0 = V.block_y0 - PTB_SVGF_HALO > 0 ? V.block_y0 - PTB_SVGF_HALO : 0;
+            V.ext_y1 = V.block_y1 + PTB_SVGF_HALO < F.height ? V.block_y1 + PTB_SVGF_HALO : F.height;
+            float4* in = F.xchg.frames[F.rank] + xchg_input_offset(S, V.parity);
+            V.in_direct = in; V.in_indirect = in + (size_t)S; V.in_albedo = in + (size_t)S * 2; V.in_normal_depth = in + (size_t)S * 3;
+            V.in_ids = reinterpret_cast<int2*>(in + (size_t)S * 4); V.in_screen_prev = reinterpret_cast<float2*>(in + (size_t)S * 4 + (size_t)S / 2);
+            for (int p = 0; p < 2; p++) {
+                float4* h = F.xchg.frames[F.rank] + xchg_history_offset(S, p);
+                V.hist[p].direct = h; V.hist[p].indirect = h + (size_t)S; V.hist[p].moment = h + (size_t)S * 2; V.hist[p].normal_depth = h + (size_t)S * 3;
+                V.hist[p].taa = h + (size_t)S * 4; V.hist[p].length = reinterpret_cast<int*>(h + (size_t)S * 5);
+            }
+        } else {
+            V.block_y0 = V.ext_y0 = 0; V.block_y1 = V.ext_y1 = F.height;
+            V.in_direct = F.aov[PTB_AOV_RADIANCE_DIRECT].fb; V.in_indirect = F.aov[PTB_AOV_RADIANCE_INDIRECT].fb; V.in_albedo = F.aov[PTB_AOV_ALBEDO].fb;
+            V.in_normal_depth = V.gbuf_normal_depth; V.in_ids = V.gbuf_ids; V.in_screen_prev = V.gbuf_screen_prev;
+            V.hist[0] = ctx->local_hist[0]; V.hist[1] = ctx->local_hist[1];
+        }
+        ctx->svgf_frames++;
     }
     if (F.config.enable_svgf && samples != 1) return PTB_E_STATE;   // SVGF is temporal: one pass per displayed frame
     cudaStream_t st = ctx->stream;
@@ -1001,6 +1023,7 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
     { StageTimer t(ctx, ST_POST);
       if (F.config.enable_svgf) {
           int e = launch_svgf(F, st, first_sample, g1d, &ctx->launches); if (e) return e;
+          if (F.xchg.svgf) ctx->xchg_frames++;
       } else {
           k_accumulate<<<g1d, 256, 0, st>>>(F); ctx->launches++;
           if (F.xchg.push) { k_exchange_wait<<<1, 1, 0, st>>>(F); ctx->launches++; }
@@ -1052,7 +1075,7 @@ extern "C" int ptb_render_frame(ptb_ctx* ctx, int first_sample_index, int num_pa
     if (!ctx || num_passes <= 0) return PTB_E_BADARG;
     if (!ctx->has_scene) return PTB_E_NOSCENE;
     CK(cudaSetDevice(ctx->device));
-    if (ctx->timing || ctx->stats_mode) {            // per-stage events are not captured into graphs
+    if (ctx->timing || ctx->stats_mode || ctx->F.config.enable_svgf) {   // per-stage events are not captured into graphs; SVGF frames alternate history parity
         if (ctx->timing) { ctx->timed.clear(); ctx->event_used = 0; }
         int e = render_passes(ctx, first_sample_index, num_passes);
         if (!e && ctx->F.xchg.count > 0 && !ctx->F.config.enable_svgf) ctx->xchg_frames++;
@@ -1163,7 +1186,6 @@ extern "C" int ptb_exchange_disconnect(ptb_ctx* ctx) {
 extern "C" int ptb_exchange_frame(ptb_ctx* ctx, void** device_ptr, int* pitch) {
     if (!ctx || !device_ptr) return PTB_E_BADARG;
     if (ctx->F.xchg.count == 0) return PTB_E_STATE;
-    if (ctx->F.config.enable_svgf) { *device_ptr = ctx->F.display; if (pitch) *pitch = ctx->F.pitch; return 0; }   // every rank filtered the whole frame
     if (ctx->xchg_frames == 0) return PTB_E_STATE;
     *device_ptr = static_cast<char*>(ctx->xchg_block) + PTB_XCHG_HEADER + (size_t)((ctx->xchg_frames - 1) & 1u) * ctx->F.fb_stride * sizeof(float4);
     if (pitch) *pitch = ctx->F.pitch;
@@ -1297,10 +1319,17 @@ extern "C" int ptb_debug_read(ptb_ctx* ctx, int which, void* host_dst, int64_t b
         CK(cudaStreamSynchronize(ctx->stream));
         return 0;
     }
-    if (which >= 10 && which <= 17) {   // SVGF state (pitch x height elements)
+    if (which >= 10 && which <= 17) {   // SVGF state (pitch x height elements) as the last filtered frame left it; with several ranks only
+                                        // the rows of this rank's filter block are meaningful
         const Frame& F = ctx->F;
-        const void* src[8] = { F.svgf.history_normal_depth, F.svgf.history_direct, F.svgf.history_indirect, F.svgf.history_moment,
-                               F.svgf.moment, F.svgf.taa_curr, F.svgf.taa_prev, F.svgf.history_length };
+        if (!F.svgf.moment || ctx->svgf_frames == 0) return PTB_E_STATE;
+        const int parity = int((ctx->svgf_frames - 1u) & 1u);
+        SVGFHistory h = ctx->local_hist[parity];
+        if (F.xchg.count > 0) {
+            float4* b = F.xchg.frames[F.rank] + xchg_history_offset(F.fb_stride, parity); const size_t S = (size_t)F.fb_stride;
+            h.direct = b; h.indirect = b + S; h.moment = b + 2 * S; h.normal_depth = b + 3 * S; h.taa = b + 4 * S; h.length = reinterpret_cast<int*>(b + 5 * S);
+        }
+        const void* src[8] = { h.normal_depth, h.direct, h.indirect, h.moment, F.svgf.moment, F.svgf.taa_curr, h.taa, h.length };
         size_t elem = which == 17 ? sizeof(int) : sizeof(float4);
         size_t need = (size_t)F.pitch * F.height * elem;
         if (!src[which - 10] || (size_t)bytes < need) return PTB_E_BADARG;

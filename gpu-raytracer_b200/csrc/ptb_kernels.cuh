@@ -1403,29 +1403,35 @@ PTB_DI bool spin_until_all(const Frame& P, const unsigned* slots, unsigned targe
         __nanosleep(200);
     }
 }
-// 1. wait until every peer has consumed (filtered + cleared) the previous frame's inputs in ITS block -- they are single-buffered
-__global__ void k_svgf_wait_consumed(const __grid_constant__ Frame P) {
-    ExchangeControl* mine = P.xchg.control[P.rank];
-    if (!spin_until_all(P, mine->svgf_consumed, mine->svgf_epoch)) mine->status = 1u;
+// Tile-local SVGF (world > 1).  Tracing is sharded by interleaved bands, filtering by contiguous blocks of rows: rank f filters rows
+// [f * rows_per_block, (f + 1) * rows_per_block) and needs the noisy inputs of those rows plus PTB_SVGF_HALO rows on either side.
+PTB_DI int svgf_block_owner(const Frame& P, int y) { int o = y / P.xchg.rows_per_block; return o < P.world ? o : P.world - 1; }
+PTB_DI void svgf_ext_range(const Frame& P, int f, int& y0, int& y1) {
+    y0 = max(0, f * P.xchg.rows_per_block - PTB_SVGF_HALO);
+    y1 = min(P.height, (f == P.world - 1 ? P.height : (f + 1) * P.xchg.rows_per_block) + PTB_SVGF_HALO);
 }
-// 2. store this rank's rows of the six input planes into every peer's block, then publish the frame number
+// 1. every rank stores the rows it TRACED (six planes, 80 B per pixel) into the input planes (this frame's parity) of every rank
+//    whose extended block contains the row -- itself included -- then publishes the frame number on every rank
 __global__ void __launch_bounds__(256) k_svgf_push(const __grid_constant__ Frame P) {
+    const int S = P.fb_stride;
+    const size_t in_off = xchg_input_offset(S, P.svgf.parity);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.local_pixels; i += gridDim.x * blockDim.x) {
         int x, y; local_to_pixel(P, i, x, y);
         size_t px = size_t(x) + size_t(y) * P.pitch;
-        const float4* mine = P.xchg.frames[P.rank];
-        float4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = mine[xchg_svgf_plane_offset(P.fb_stride, k) + px];
-        float2 ids = reinterpret_cast<const float2*>(mine + xchg_svgf_plane_offset(P.fb_stride, 4))[px];
-        float2 sp  = reinterpret_cast<const float2*>(mine + xchg_svgf_plane_offset(P.fb_stride, 5))[px];
-        for (int r = 0; r < P.xchg.count; r++) {
-            if (r == P.rank) continue;
-            float4* dst = P.xchg.frames[r];
-#pragma unroll
-            for (int k = 0; k < 4; k++) dst[xchg_svgf_plane_offset(P.fb_stride, k) + px] = v[k];
-            reinterpret_cast<float2*>(dst + xchg_svgf_plane_offset(P.fb_stride, 4))[px] = ids;
-            reinterpret_cast<float2*>(dst + xchg_svgf_plane_offset(P.fb_stride, 5))[px] = sp;
+        float4 v0 = P.aov[PTB_AOV_RADIANCE_DIRECT].fb[px], v1 = P.aov[PTB_AOV_RADIANCE_INDIRECT].fb[px], v2 = P.aov[PTB_AOV_ALBEDO].fb[px];
+        float4 v3 = P.svgf.gbuf_normal_depth[px];
+        int2 ids = P.svgf.gbuf_ids[px];
+        float2 sp = P.svgf.gbuf_screen_prev[px];
+        // the filter chain clears nothing on this side any more: the trace-side planes start the next frame empty
+        P.aov[PTB_AOV_RADIANCE_DIRECT].fb[px] = f4(0.0f); P.aov[PTB_AOV_RADIANCE_INDIRECT].fb[px] = f4(0.0f); P.aov[PTB_AOV_ALBEDO].fb[px] = f4(0.0f);
+        P.svgf.gbuf_normal_depth[px] = f4(0.0f); P.svgf.gbuf_ids[px] = make_int2(0, 0); P.svgf.gbuf_screen_prev[px] = f2(0.0f, 0.0f);
+        for (int f = 0; f < P.world; f++) {
+            int y0, y1; svgf_ext_range(P, f, y0, y1);
+            if (y < y0 || y >= y1) continue;
+            float4* dst = P.xchg.frames[f] + in_off;
+            dst[px] = v0; dst[size_t(S) + px] = v1; dst[size_t(S) * 2 + px] = v2; dst[size_t(S) * 3 + px] = v3;
+            reinterpret_cast<int2*>(dst + size_t(S) * 4)[px] = ids;
+            reinterpret_cast<float2*>(dst + size_t(S) * 4 + size_t(S) / 2)[px] = sp;
         }
     }
     __threadfence_system();
@@ -1441,17 +1447,36 @@ __global__ void __launch_bounds__(256) k_svgf_push(const __grid_constant__ Frame
         }
     }
 }
-// 3. wait for every rank's rows, advance the epoch
+// 2. wait for every rank's rows of this frame (which also means: every rank has finished filtering the previous frame, so the
+//    history it owns is complete and nobody still reads the parity this frame overwrites), advance the epoch
 __global__ void k_svgf_wait_arrivals(const __grid_constant__ Frame P) {
     ExchangeControl* mine = P.xchg.control[P.rank];
     if (!spin_until_all(P, mine->svgf_arrivals, mine->svgf_epoch + 1u)) mine->status = 1u;
     mine->svgf_epoch += 1u;
 }
-// 4. after the filter chain (which ends by clearing the planes): tell every peer this rank's block may be written again
-__global__ void k_svgf_signal_consumed(const __grid_constant__ Frame P) {
-    ExchangeControl* mine = P.xchg.control[P.rank];
+// 3. after the filter chain: the displayed rows of this rank's block go to every rank's gathered frame (same protocol and
+//    counters as the accumulate kernel's fused gather; k_exchange_wait closes the frame)
+__global__ void __launch_bounds__(256) k_svgf_push_display(const __grid_constant__ Frame P) {
+    const size_t plane = size_t(P.xchg.control[P.rank]->epoch & 1u) * size_t(P.fb_stride);
+    const int rows = P.svgf.block_y1 - P.svgf.block_y0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * P.width; i += gridDim.x * blockDim.x) {
+        int y = P.svgf.block_y0 + i / P.width, x = i % P.width;
+        size_t px = size_t(x) + size_t(y) * P.pitch;
+        float4 c = P.display[px];
+        for (int r = 0; r < P.xchg.count; r++) P.xchg.frames[r][plane + px] = c;
+    }
     __threadfence_system();
-    for (int r = 0; r < P.xchg.count; r++) st_release_sys(&P.xchg.control[r]->svgf_consumed[P.rank], mine->svgf_epoch);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ExchangeControl* mine = P.xchg.control[P.rank];
+        unsigned done = atomicAdd(&mine->blocks_done, 1u);
+        if (done == gridDim.x - 1) {
+            mine->blocks_done = 0;
+            __threadfence_system();
+            const unsigned frame_no = mine->epoch + 1u;
+            for (int r = 0; r < P.xchg.count; r++) st_release_sys(&P.xchg.control[r]->arrivals[P.rank], frame_no);
+        }
+    }
 }
 
 // tile export / assemble for the multi-GPU gather

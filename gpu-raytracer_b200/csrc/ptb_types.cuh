@@ -80,21 +80,42 @@ struct TextureEntry {                 // 16 bytes, Integrator.h:129-132
     float pad;
 };
 
+// Temporal state of SVGF + TAA, one parity.  The filter of frame k writes hist[k & 1] and reads hist[(k - 1) & 1]; with several ranks
+// every rank filters -- and owns the history of -- one contiguous block of rows, and reads of the previous parity go to the OWNER of
+// the row (peer memory), see ptb_svgf.cuh.
+struct SVGFHistory {
+    float4* direct;
+    float4* indirect;
+    float4* moment;
+    float4* normal_depth;
+    float4* taa;                      // taa_frame_prev
+    int*    length;
+};
 struct SVGFBuffers {
+    // trace side: written by k_sort / k_shade at the rows this rank TRACES (interleaved bands)
     float4* gbuf_normal_depth;        // (oct normal.xy, depth, depth gradient)
     int2*   gbuf_ids;                 // (mesh id, triangle id)
     float2* gbuf_screen_prev;         // previous-frame screen position
+    // filter side: what the filter chain of this rank reads.  world == 1: the trace-side planes themselves; world > 1: planes in
+    // this rank's exchange block that every tracing rank stores its rows into (k_svgf_push)
+    float4* in_direct;
+    float4* in_indirect;
+    float4* in_albedo;
+    float4* in_normal_depth;
+    int2*   in_ids;
+    float2* in_screen_prev;
     float4* moment;                   // frame_buffer_moment
-    int*    history_length;
-    float4* history_direct;
-    float4* history_indirect;
-    float4* history_moment;
-    float4* history_normal_depth;
-    float4* taa_prev;
     float4* taa_curr;
+    SVGFHistory hist[2];
+    int     parity;                   // hist[parity] is written this frame, hist[parity ^ 1] is last frame's
+    int     block_y0, block_y1;       // rows this rank filters and whose history it owns
+    int     ext_y0, ext_y1;           // block + halo (PTB_SVGF_HALO rows each side, clipped): rows the filter chain is evaluated on
     float   view_projection[16];
     float   view_projection_prev[16];
 };
+// Rows of halo a filter block needs around it so that its own rows come out exactly as a whole-frame filter computes them:
+// TAA 1 + a-trous strides 32+16+8+4+2+1 + variance blur 1 + 7x7 variance 3 + depth gradient 1 = 69 (SVGF.h:284-554); rounded up.
+#define PTB_SVGF_HALO 72
 
 // Frame exchange over NVLink peer memory (multi-GPU).  Every rank owns one block {2 full frames, control words};
 // the blocks of all ranks are mapped into every rank (CUDA IPC between processes, plain peer access inside one).  The last
@@ -108,10 +129,9 @@ struct ExchangeControl {
     unsigned blocks_done;             // local: CTAs of k_accumulate that finished storing
     unsigned epoch;                   // local: frames completed
     unsigned status;                  // local: 0 ok, 1 = wait timed out
-    // SVGF input exchange (k_svgf_push): the same protocol on its own counters, plus a "consumed" handshake because the planes
-    // are single-buffered (a rank may only store frame k+1 into a peer once that peer has filtered AND cleared frame k)
+    // SVGF input exchange (k_svgf_push): the same protocol on its own counters.  The input planes are double-buffered by frame
+    // parity; a rank cannot run two frames ahead of a peer (its own filter of frame k+1 needs that peer's rows of frame k+1)
     unsigned svgf_arrivals[PTB_MAX_PEERS];
-    unsigned svgf_consumed[PTB_MAX_PEERS];   // slot s: frames rank s has finished consuming
     unsigned svgf_blocks_done;
     unsigned svgf_epoch;
 };
@@ -120,14 +140,19 @@ struct Exchange {
     int     push;                     // this launch is the last accumulate of a frame: store to the peers
     float4* frames[PTB_MAX_PEERS];    // peer-mapped base of rank r's block: frame parity p at frames[r] + p * pitch * height
     ExchangeControl* control[PTB_MAX_PEERS];
-    // SVGF with world > 1: the noisy inputs of the filter (3 float4 AOV framebuffers + 3 g-buffers, 80 B per pixel) live in the
-    // exchange block behind the two frames; every rank stores its rows into every peer, then runs the filter on the whole frame.
-    int     svgf;                     // this pass exchanges the SVGF inputs
+    // SVGF with world > 1 (tile-local filter): behind the two frames every block carries, per parity, the six filter-input planes
+    // (stored into by the tracing ranks) and the temporal history planes of the rows this rank owns (read by its neighbours)
+    int     svgf;                     // this pass runs the tile-local filter over the exchange blocks
+    int     rows_per_block;           // filter block height: rank r owns rows [r * rows_per_block, (r + 1) * rows_per_block)
 };
 #define PTB_XCHG_HEADER 512
-// plane k of the SVGF inputs inside rank r's block (float4 units from frames[r]); planes 0..3 are float4, 4 and 5 are 8-byte
-__host__ __device__ inline size_t xchg_svgf_plane_offset(int fb_stride, int k) { return size_t(fb_stride) * (2 + (k < 4 ? k : 4)) + (k == 5 ? size_t(fb_stride) / 2 : 0); }
-#define PTB_XCHG_BLOCK_FLOAT4(fb_stride) (size_t(fb_stride) * 7)     // 2 frames + 4 float4 planes + 2 half planes
+// Layout of a block behind the header, in float4 units (S = pitch * height, a multiple of 32):
+//   [0, 2S)                       the two gathered frames
+//   inputs of parity p  at 2S + p * 5S:        direct S | indirect S | albedo S | normal_depth S | ids S/2 | screen_prev S/2
+//   history of parity p at 12S + p * 5.25S:    direct S | indirect S | moment S | normal_depth S | taa S | length S/4
+__host__ __device__ inline size_t xchg_input_offset(int S, int parity) { return size_t(S) * 2 + size_t(parity) * (size_t(S) * 5); }
+__host__ __device__ inline size_t xchg_history_offset(int S, int parity) { return size_t(S) * 12 + size_t(parity) * (size_t(S) * 5 + size_t(S) / 4); }
+#define PTB_XCHG_BLOCK_FLOAT4(S) (size_t(S) * 12 + 2 * (size_t(S) * 5 + size_t(S) / 4))
 
 struct Frame {
     // film + tile ownership (rows are dealt to ranks in interleaved bands)

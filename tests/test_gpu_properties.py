@@ -273,15 +273,25 @@ def test_static_merge_follows_instance_updates():
         assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
 
 
-def test_svgf_taa_sharded_equals_single_gpu():
-    """BASELINE configs[4] shape (SVGF + TAA, tile-sharded): world=3 ranks trace their row bands, store the noisy filter inputs
-    (direct / indirect / albedo framebuffers + 3 g-buffers) into each other's exchange blocks over peer memory, and every rank
-    filters the whole frame.  Display and every temporal history buffer stay bit-identical to the 1-GPU run over 5 frames with
-    a moving camera."""
-    d = scene.procedural_scene("atrium", seed=3, width=320, height=184, detail=0.5)
+def _exchange_frame_host(p, like):
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    got = np.empty_like(like)
+    assert rt.cudaMemcpy(ctypes.c_void_p(got.ctypes.data), ctypes.c_void_p(p.exchange_frame()), ctypes.c_size_t(got.nbytes), 2) == 0
+    return got
+
+
+@pytest.mark.parametrize("width,height,world", [(320, 184, 3), (256, 400, 2)])
+def test_svgf_taa_sharded_equals_single_gpu(width, height, world):
+    """BASELINE configs[4] shape (SVGF + TAA, tile-sharded).  Tracing is sharded by interleaved 8-row bands, FILTERING by contiguous
+    blocks of rows: every rank stores the rows it traced into the input planes of the ranks that filter them (block + 72-row halo),
+    filters only its block, reads last frame's history across block borders from the owning rank over peer memory, and ships its
+    displayed rows to everybody.  The gathered frame on every rank and the temporal buffers of every rank's block stay bit-identical
+    to the 1-GPU run over 6 frames with a moving camera (reprojection crosses block borders).  Second case: blocks taller than the
+    halo (the production shape)."""
+    d = scene.procedural_scene("atrium", seed=3, width=width, height=height, detail=0.5)
     blob = scene.build_blob(d, 8, rng="fallback")
     cfg = pt.default_config(num_bounces=3, enable_svgf=1, enable_taa=1)
-    world = 3
     whole = pt.Pathtracer(blob, config=cfg)
     ranks = [pt.Pathtracer(blob, rank=r, world=world, band_rows=8, config=cfg) for r in range(world)]
     bases = [p.exchange_create()[0] for p in ranks]
@@ -291,9 +301,9 @@ def test_svgf_taa_sharded_equals_single_gpu():
     for p in [whole] + ranks:
         p.update()                     # uploads the config (allocations synchronise the device: keep them out of the frame loop,
                                        # where a rank's frame ends in a device-side wait for peers that share this GPU)
-    for frame in range(5):
-        if frame in (2, 3):
-            cam = cam.copy(); cam[0] += 0.05
+    for frame in range(6):
+        if frame in (2, 3, 4):
+            cam = cam.copy(); cam[0] += 0.05; cam[1] += 0.03 * (frame - 2)          # sideways and up / down: history taps move across rows
             for p in [whole] + ranks:
                 p.set_camera(cam)
         if frame > 0:
@@ -306,11 +316,14 @@ def test_svgf_taa_sharded_equals_single_gpu():
             p.sync()
         want = whole.get_display()
         for p in ranks:
-            assert np.array_equal(p.get_display()[:, :320].view(np.uint32), want[:, :320].view(np.uint32)), (frame, p.rank)
-    for name in ("history_direct", "history_indirect", "history_moment", "history_length", "taa_frame_prev"):
+            got = _exchange_frame_host(p, want)
+            assert np.array_equal(got[:, :width].view(np.uint32), want[:, :width].view(np.uint32)), (frame, p.rank)
+    rows_per_block = -(-height // world)
+    for name in ("history_direct", "history_indirect", "history_moment", "history_normal_and_depth", "history_length", "taa_frame_prev"):
         want = whole.svgf_buffer(name)
         for p in ranks:
-            assert np.array_equal(p.svgf_buffer(name)[:, :320], want[:, :320]), name
+            y0 = p.rank * rows_per_block; y1 = height if p.rank == world - 1 else min(height, (p.rank + 1) * rows_per_block)
+            assert np.array_equal(p.svgf_buffer(name)[y0:y1, :width], want[y0:y1, :width]), (name, p.rank)
     for p in ranks:
         p.close()
     whole.close()
