@@ -280,7 +280,7 @@ def run_reference(args, blob, workload):
     st = r.ray_stats(reset=True)
     rays = int(st["trace"].sum() + st["shadow"].sum())
     # e2e: + read-back of every displayed frame to pinned host memory, double-buffered behind the next frame (as in the product arm)
-    step(download=True); r.wait_display_download(dl_no[0] & 1)
+    step(download=True); step(download=True); r.wait_display_download(dl_no[0] & 1)
     r.sync(); r.ray_stats(reset=True)
     t0 = time.perf_counter()
     for _ in range(args.steps):

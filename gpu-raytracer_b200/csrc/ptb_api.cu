@@ -100,7 +100,8 @@ struct ptb_ctx {
     bool overlap_enabled = true;
     // static merge: identity-transform instances re-built into ONE CWBVH at upload (rebuild_static_merge)
     bool merge_enabled = true;
-    bool merge_spatial = true;                        // merged BVH built with spatial splits (SBVH); false = plain full-sweep SAH
+    bool merge_spatial = true;
+    bool half_nodes = true;                           // conservative packed-half node test outside the bit-exact mode (A/B: PTB_HALF_NODES=0)                        // merged BVH built with spatial splits (SBVH); false = plain full-sweep SAH
     std::vector<unsigned char> host_nodes;            // node array as uploaded by the host (for leaf walks)
     std::vector<float4> host_tri_pos;                 // first 3 float4 of every triangle record
     std::vector<int> host_roots;                      // roots as last given by the host
@@ -264,7 +265,8 @@ __global__ void __launch_bounds__(1024) k_apply_uploads(const unsigned char* are
 template <typename K> static void preload(K kernel) { cudaFuncAttributes a; cudaFuncGetAttributes(&a, kernel); }
 static void preload_kernels() {
     preload(k_generate); preload(k_begin_pass); preload(k_fold_counters); preload(k_sort); preload(k_accumulate);
-    preload(k_trace8<false, false>); preload(k_trace8<true, false>); preload(k_trace8<false, true>); preload(k_trace8<true, true>);
+    preload(k_trace8<false, false, true>); preload(k_trace8<true, false, true>); preload(k_trace8<false, true, true>); preload(k_trace8<true, true, true>);
+    preload(k_trace8<false, false, false>); preload(k_trace8<true, false, false>); preload(k_trace8<false, true, false>); preload(k_trace8<true, true, false>);
     preload(k_trace2<false, false>); preload(k_trace2<true, false>); preload(k_trace2<false, true>); preload(k_trace2<true, true>);
     preload(k_shade<BSDFDiffuse>); preload(k_shade<BSDFPlastic>); preload(k_shade<BSDFDielectric>); preload(k_shade<BSDFConductor>);
     preload(k_bin_count<false>); preload(k_bin_count<true>); preload(k_bin_scatter<false>); preload(k_bin_scatter<true>);
@@ -292,6 +294,7 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     if (const char* v = getenv("PTB_TRACE_OVERLAP")) ctx->overlap_enabled = atoi(v) != 0;     // A/B switch for tools/, default on
+    if (const char* v = getenv("PTB_HALF_NODES")) ctx->half_nodes = atoi(v) != 0;
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
@@ -322,10 +325,14 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     { int fe = allocate_film(ctx); if (fe) { ptb_destroy(ctx); return fe; } }
 
     preload_kernels();
-    CKC(cudaFuncSetAttribute(k_trace8<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CKC(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return 0;
@@ -936,6 +943,17 @@ struct StageTimer {
 
 static size_t trace8_smem() { return 16 + (size_t)PTB_TLAS_STAGE_MAX_NODES * 80 + (size_t)PTB_SM_STACK * PTB_TRACE_BLOCK * sizeof(uint2); }
 
+// which node test a launch uses: the float one whenever bit parity is promised (static merge off = the reference's two-level walk),
+// the conservative packed-half one otherwise (if built in: PTB_NODE_HALF)
+template <bool SHADOW>
+static void launch_trace8(ptb_ctx* ctx, const Frame& F, int grid, cudaStream_t st, int bounce, const unsigned* order) {
+    const bool exact = !(PTB_NODE_HALF && ctx->merge_enabled && ctx->half_nodes);
+    if (exact) { if (ctx->stats_mode) k_trace8<SHADOW, true, true><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order);
+                 else                 k_trace8<SHADOW, false, true><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order); }
+    else       { if (ctx->stats_mode) k_trace8<SHADOW, true, false><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order);
+                 else                 k_trace8<SHADOW, false, false><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order); }
+}
+
 // One wave: `samples` consecutive passes (first_sample ...) through the whole pipeline.  The role of one or several
 // Pathtracer::render() calls (Pathtracer.cpp:738-855); asynchronous, no host<->device synchronisation.
 static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = false) {
@@ -993,8 +1011,7 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
         if (order_c) { StageTimer t(ctx, ST_ORDER);
           k_bin_count<false><<<g1d, 256, 0, st>>>(F, bounce); k_bin_scatter<false><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches += 2; }
         { StageTimer t(ctx, ST_TRACE);
-          if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<false, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order_c);
-                                    else                 k_trace8<false, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order_c); }
+          if (ctx->bvh_kind == 8) { launch_trace8<false>(ctx, F, gtrace, st, bounce, order_c); }
           else if (ctx->stats_mode) k_trace2<false, true><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
           else                    k_trace2<false, false><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
           ctx->launches++; }
@@ -1011,8 +1028,7 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
             StageTimer t(ctx, ST_SHADOW);
             cudaStream_t ss = st;
             if (overlap) { CK(cudaEventRecord(ctx->ev_fork, st)); CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0)); ss = ctx->side_stream; }
-            if (ctx->bvh_kind == 8) { if (ctx->stats_mode) k_trace8<true, true><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), ss>>>(F, bounce, order_s);
-                                      else                 k_trace8<true, false><<<gtrace, PTB_TRACE_BLOCK, trace8_smem(), ss>>>(F, bounce, order_s); }
+            if (ctx->bvh_kind == 8) { launch_trace8<true>(ctx, F, gtrace, ss, bounce, order_s); }
             else if (ctx->stats_mode) k_trace2<true, true><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce);
             else                    k_trace2<true, false><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce);
             ctx->launches++;

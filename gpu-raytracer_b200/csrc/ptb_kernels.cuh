@@ -29,14 +29,8 @@
 #ifndef PTB_SHADE_MIN_BLOCKS_DIFFUSE
 #define PTB_SHADE_MIN_BLOCKS_DIFFUSE 4    // 64 registers (120 B of spills) but twice the gathers in flight: frame 32.72 -> 32.21 ms
 #endif
-#ifndef PTB_DEFER_TRIS
-#define PTB_DEFER_TRIS 0                  // (1:) triangle tests wait in a per-lane register until enough lanes have one (k_trace8)
-#endif
-#ifndef PTB_DEFER_NUM
-#define PTB_DEFER_NUM 3                   // ... "enough" = PTB_DEFER_NUM / PTB_DEFER_DEN of the live lanes
-#endif
-#ifndef PTB_DEFER_DEN
-#define PTB_DEFER_DEN 8
+#ifndef PTB_NODE_HALF
+#define PTB_NODE_HALF 0                   // (1:) default traversal mode uses the conservative packed-half node test
 #endif
 #ifndef PTB_TILED_GENERATE
 #define PTB_TILED_GENERATE 1              // primary rays enumerated so that a warp covers an 8x4 pixel tile (not a 32x1 strip)
@@ -190,10 +184,6 @@ PTB_DI void stack_push(const TraceShared& S, uint2* local, int& sp, uint2 v) {
     if (sp < PTB_SM_STACK) S.stack[sp * PTB_TRACE_BLOCK + threadIdx.x] = v; else local[sp - PTB_SM_STACK] = v;
     sp++;
 }
-PTB_DI uint2 stack_peek(const TraceShared& S, const uint2* local, int sp) {
-    sp--;
-    return sp < PTB_SM_STACK ? S.stack[sp * PTB_TRACE_BLOCK + threadIdx.x] : local[sp - PTB_SM_STACK];
-}
 PTB_DI uint2 stack_pop(const TraceShared& S, const uint2* local, int& sp) {
     sp--;
     return sp < PTB_SM_STACK ? S.stack[sp * PTB_TRACE_BLOCK + threadIdx.x] : local[sp - PTB_SM_STACK];
@@ -201,7 +191,8 @@ PTB_DI uint2 stack_pop(const TraceShared& S, const uint2* local, int& sp) {
 
 // STATS = true additionally counts node visits / triangle tests / instance transforms per ray kind (roofline accounting:
 // algorithmic bytes = 80 B per node + 48 B per triangle + 48 B per instance transform + the ray/hit streams).
-template <bool SHADOW, bool STATS>
+// EXACT = true: the reference's float node test (bit-exact mode); false: the conservative packed-half test (ptb_device.cuh).
+template <bool SHADOW, bool STATS, bool EXACT>
 __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace8(const __grid_constant__ Frame P, int bounce, const unsigned* __restrict__ order) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -225,7 +216,6 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
     uint2 local_stack[PTB_LOCAL_STACK];
     int sp = 0;
     uint2 cur = make_uint2(0, 0);
-    uint2 pend = make_uint2(0, 0);          // triangle group waiting to be tested (PTB_DEFER_TRIS)
     int ray_index = 0;
     Ray ray; ray.o = f3(0.0f); ray.d = f3(1.0f);
     unsigned oct4 = 0;
@@ -251,7 +241,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                     else        { a = q.od0[ray_index];    b = q.od1[ray_index];    hit.t = PTB_INF; hit.triangle_id = PTB_INVALID; }
                     ray.o = f3(a.x, a.y, a.z); ray.d = f3(a.w, b.x, b.y);
                     oct4 = ray_octant_inv4(ray.d);
-                    sp = 0; live = true; pend = make_uint2(0, 0);
+                    sp = 0; live = true;
                     if (P.flat_root >= 0) {
                         // merged static BVH first (it sets a tight hit.t early); the TLAS root waits on the stack for what is not merged
                         if (!P.flat_all) stack_push(S, local_stack, sp, make_uint2(0u, 0x80000000u));
@@ -280,143 +270,6 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
             return;
         }
 
-#if PTB_DEFER_TRIS
-        // Triangle hits of a node are not tested in the iteration that found them: they wait in a per-lane register (`pend`) and the
-        // warp tests ONE triangle per waiting lane only when enough lanes wait (or a lane has nothing else left to do).  The
-        // reference (BVH8.h:233-246) tests as soon as 20 % of the lanes want to and otherwise postpones through the stack; measured on
-        // the B200 that loop ran 1.65 times per node step with 7.8 of 32 lanes active (profiles/r2_trace8_notes.md) -- a quarter of
-        // the kernel's issue slots.  Results do not depend on when a triangle is tested (closest hit: min over the same set).
-        int lost = 0;
-        while (true) {
-            uint2 ntri = make_uint2(0, 0);            // triangle / instance hits produced by this iteration
-            if (live) {
-                if (cur.y & 0xff000000u) {
-                    unsigned hits_imask = cur.y;
-                    unsigned child_off = msb(hits_imask);
-                    unsigned child_base = cur.x;
-                    cur.y &= ~(1u << child_off);
-                    if (cur.y & 0xff000000u) stack_push(S, local_stack, sp, cur);
-                    unsigned slot = (child_off - 24u) ^ (oct4 & 0xffu);
-                    unsigned rel = __popc(hits_imask & ~(0xffffffffu << slot));
-                    unsigned ni = child_base + rel;
-                    float4 n0, n1, n2, n3, n4;
-                    if (ni - S.stage_base < unsigned(S.staged)) {
-                        const float4* n = S.tlas + 5 * (ni - S.stage_base);
-                        n0 = n[0]; n1 = n[1]; n2 = n[2]; n3 = n[3]; n4 = n[4];
-                    } else {
-                        const float4* n = P.nodes8 + 5 * size_t(ni);
-                        n0 = __ldg(n); n1 = __ldg(n + 1); n2 = __ldg(n + 2); n3 = __ldg(n + 3); n4 = __ldg(n + 4);
-                    }
-                    if (STATS) st_nodes++;
-                    unsigned hm = cwbvh_node_intersect(ray, oct4, hit.t, n0, n1, n2, n3, n4);
-                    unsigned imask = byte_of(__float_as_uint(n0.w), 3);
-                    cur.x = __float_as_uint(n1.x);
-                    ntri.x = __float_as_uint(n1.y);
-                    cur.y = (hm & 0xff000000u) | imask;
-                    ntri.y = hm & 0x00ffffffu;
-                } else if (cur.y != 0 && tlas_sp == PTB_INVALID) {      // an instance group came off the stack (TLAS level)
-                    ntri = cur; cur = make_uint2(0, 0);
-                }
-            }
-            // TLAS level: a "triangle" is an instance; enter its BLAS (BVH8.h:204-232).  Never deferred.
-            if (live && ntri.y != 0 && tlas_sp == PTB_INVALID) {
-                unsigned off = msb(ntri.y);
-                ntri.y &= ~(1u << off);
-                int inst = int(ntri.x + off);
-                unsigned root = unsigned(__ldg(P.mesh_roots + inst));
-                if (ntri.y != 0) stack_push(S, local_stack, sp, ntri);
-                ntri.y = 0;
-                if (!(root & PTB_ROOT_MERGED)) {
-                    mesh_id = inst;
-                    if (cur.y & 0xff000000u) stack_push(S, local_stack, sp, cur);
-                    tlas_sp = sp;
-                    identity = (root & PTB_ROOT_IDENTITY) != 0;
-                    if (!identity) {
-                        Mat3x4 inv = load_mat(P.mesh_transforms_inv, mesh_id);
-                        ray.o = xform_pos(inv, ray.o);
-                        ray.d = xform_dir(inv, ray.d);
-                        oct4 = ray_octant_inv4(ray.d);
-                        if (STATS) st_xf++;
-                    }
-                    cur = make_uint2(root & 0x3fffffffu, 0x80000000u);
-                }
-            }
-            // new triangle hits: into the pending register, or (register busy) onto the stack as a postponed group
-            if (live && ntri.y != 0) {
-                if (pend.y == 0) pend = ntri; else stack_push(S, local_stack, sp, ntri);
-            }
-            // What comes next for a lane whose node group is exhausted?  Ending the ray or leaving the current BLAS needs an empty
-            // pending register (those triangles belong to THIS instance and THIS ray transform); so does taking a postponed
-            // triangle group off the stack.  Such a lane is blocked on triangles and forces a test round now.
-            const bool exhausted_group = live && (cur.y & 0xff000000u) == 0;
-            const bool at_boundary = sp == 0 || sp == tlas_sp;
-            uint2 top = make_uint2(0, 0);
-            if (exhausted_group && !at_boundary) top = stack_peek(S, local_stack, sp);
-            const bool top_is_tri = exhausted_group && !at_boundary && (top.y & 0xff000000u) == 0 && tlas_sp != PTB_INVALID;
-            const bool blocked = exhausted_group && pend.y != 0 && (at_boundary || top_is_tri);
-            const unsigned wanting = __ballot_sync(FULL, live && pend.y != 0);
-            const unsigned alive_now = __ballot_sync(FULL, live);
-            bool terminated = false;
-            if (wanting != 0 && (__any_sync(FULL, blocked) || __popc(wanting) * PTB_DEFER_DEN >= __popc(alive_now) * PTB_DEFER_NUM)) {
-                if (live && pend.y != 0) {
-                    unsigned ti = msb(pend.y);
-                    pend.y &= ~(1u << ti);
-                    if (STATS) st_tris++;
-                    if (SHADOW) {
-                        if (occludes_triangle(P, mesh_id, int(pend.x + ti), ray, hit.t)) { terminated = true; pend.y = 0; }
-                    } else {
-                        intersect_triangle(P, mesh_id, int(pend.x + ti), ray, hit);
-                    }
-                }
-            }
-            if (live) {
-                if (SHADOW && terminated) {
-                    live = false; sp = 0; cur = make_uint2(0, 0); pend = make_uint2(0, 0);      // occluded: drop the ray
-                } else if (exhausted_group) {
-                    if (at_boundary) {
-                        if (pend.y != 0) {
-                            cur = make_uint2(0, 0);                                              // still blocked: try again next iteration
-                        } else if (sp == 0) {
-                            if (SHADOW) {
-                                // unoccluded: deposit the light sample (Pathtracer.cu:183-196)
-                                if (STATS) st_miss++;
-                                float4 ill = P.sq.illum[ray_index];
-                                int px = word_fb_index(P, __float_as_uint(P.sq.od1[ray_index].w));
-                                float4 v = make_float4(ill.x, ill.y, ill.z, 0.0f);
-                                aov_add(P, PTB_AOV_RADIANCE, px, v);
-                                if (bounce == 0) aov_set(P, PTB_AOV_RADIANCE_DIRECT, px, v);
-                                else             aov_add(P, PTB_AOV_RADIANCE_INDIRECT, px, v);
-                            } else {
-                                if (hit.mesh_id < -1) hit.mesh_id = __ldg(P.flat_slot_instance + (-(hit.mesh_id) - 2));   // merged slot -> instance
-                                q.hit[ray_index] = pack_hit(hit);
-                            }
-                            live = false; cur = make_uint2(0, 0);
-                        } else {
-                            tlas_sp = PTB_INVALID;
-                            if (!identity) {   // back to world space: re-read the ray (L2 resident) instead of holding 6 registers
-                                float4 a = SHADOW ? P.sq.od0[ray_index] : q.od0[ray_index];
-                                float4 b = SHADOW ? P.sq.od1[ray_index] : q.od1[ray_index];
-                                ray.o = f3(a.x, a.y, a.z); ray.d = f3(a.w, b.x, b.y);
-                                oct4 = ray_octant_inv4(ray.d);
-                            }
-                            cur = stack_pop(S, local_stack, sp);
-                        }
-                    } else if (top_is_tri) {
-                        if (pend.y == 0) { pend = top; sp--; }                                   // postponed triangles: into the register
-                        cur = make_uint2(0, 0);
-                    } else {
-                        cur = top; sp--;
-                    }
-                }
-            }
-            unsigned alive = __ballot_sync(FULL, live);
-            if (alive == 0) break;
-            lost += 32 - __popc(alive) - PTB_DYNFETCH_ND;
-            if (lost >= PTB_DYNFETCH_NW) break;
-        }
-    }
-}
-#else
         int lost = 0;
         while (true) {
             uint2 tri = make_uint2(0, 0);
@@ -439,7 +292,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                         n0 = __ldg(n); n1 = __ldg(n + 1); n2 = __ldg(n + 2); n3 = __ldg(n + 3); n4 = __ldg(n + 4);
                     }
                     if (STATS) st_nodes++;
-                    unsigned hm = cwbvh_node_intersect(ray, oct4, hit.t, n0, n1, n2, n3, n4);
+                    unsigned hm = EXACT ? cwbvh_node_intersect(ray, oct4, hit.t, n0, n1, n2, n3, n4) : cwbvh_node_intersect_half(ray, oct4, hit.t, n0, n1, n2, n3, n4);
                     unsigned imask = byte_of(__float_as_uint(n0.w), 3);
                     cur.x = __float_as_uint(n1.x);
                     tri.x = __float_as_uint(n1.y);
@@ -535,7 +388,6 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
         }
     }
 }
-#endif
 
 // ------------------------------------------------------------------------------------------ binary BVH traversal (config 1)
 // Src/CUDA/Raytracing/BVH2.h:4-244: ordered descent by split axis, TLAS leaf = instance.

@@ -761,6 +761,10 @@ void* ptbh_build_triangles_sbvh(const float* pos, int n, float alpha, int bins, 
 // CPU closest-hit walk of a built CWBVH (tuning / test aid: visit counts per ray predict the device kernel's work; BVH8.h:113-274
 // semantics: octant-ordered child pops, triangles of a node tested before descending, culling against the current closest hit).
 // rays: n x 6 floats (origin, direction).  Adds the visits to counts[0] (nodes) and counts[1] (triangle tests); hit_t / hit_tri may be null.
+// optional sink for ptbh_trace_stats: (ray index, node index, closest hit so far) of every node visit, up to `capacity` records
+static int* g_visit_ray = nullptr; static int* g_visit_node = nullptr; static float* g_visit_t = nullptr; static long long g_visit_cap = 0, g_visit_n = 0;
+void ptbh_set_visit_sink(int* ray, int* node, float* t, long long capacity) { g_visit_ray = ray; g_visit_node = node; g_visit_t = t; g_visit_cap = capacity; g_visit_n = 0; }
+long long ptbh_visit_count() { return g_visit_n; }
 void ptbh_trace_stats(void* h, const float* pos, const float* rays, int n_rays, unsigned long long* counts, float* hit_t, int* hit_tri) {
     Built* b = static_cast<Built*>(h);
     const std::vector<Node8>& nodes = b->bvh8.nodes; const std::vector<int>& idx = b->bvh8.indices;
@@ -784,6 +788,7 @@ void ptbh_trace_stats(void* h, const float* pos, const float* rays, int n_rays, 
                 unsigned rel = unsigned(__builtin_popcount(imask_hits & ~(0xffffffffu << slot)));
                 const Node8& nd = nodes[cur.base + rel];
                 n_nodes++;
+                if (g_visit_ray && g_visit_n < g_visit_cap) { g_visit_ray[g_visit_n] = r; g_visit_node[g_visit_n] = int(cur.base + rel); g_visit_t[g_visit_n] = best; g_visit_n++; }
                 float ex, ey, ez; uint32_t u;
                 u = uint32_t(nd.e[0]) << 23; std::memcpy(&ex, &u, 4); u = uint32_t(nd.e[1]) << 23; std::memcpy(&ey, &u, 4); u = uint32_t(nd.e[2]) << 23; std::memcpy(&ez, &u, 4);
                 float aix = ex / dx, aiy = ey / dy, aiz = ez / dz;

@@ -616,11 +616,11 @@ int ref_e2e_begin_download(ref_ctx* c, int slot) {
     if (slot < 0 || slot > 1) return 1;
     const size_t bytes = (size_t)c->pitch * c->height * 16;
     if (!c->copy_stream) RCK(cuStreamCreate(&c->copy_stream, CU_STREAM_NON_BLOCKING));
-    if (!c->e2e_stage[slot]) {
-        RCK(cuMemAlloc(&c->e2e_stage[slot], bytes)); c->allocs.push_back(c->e2e_stage[slot]);
-        RCK(cuMemAllocHost(&c->e2e_host[slot], bytes));
-        RCK(cuEventCreate(&c->e2e_rendered[slot], CU_EVENT_DISABLE_TIMING));
-        RCK(cuEventCreate(&c->e2e_done[slot], CU_EVENT_DISABLE_TIMING));
+    for (int k = 0; k < 2; k++) if (!c->e2e_stage[k]) {           // both slots at once: no allocation ever lands inside a timed loop
+        RCK(cuMemAlloc(&c->e2e_stage[k], bytes)); c->allocs.push_back(c->e2e_stage[k]);
+        RCK(cuMemAllocHost(&c->e2e_host[k], bytes));
+        RCK(cuEventCreate(&c->e2e_rendered[k], CU_EVENT_DISABLE_TIMING));
+        RCK(cuEventCreate(&c->e2e_done[k], CU_EVENT_DISABLE_TIMING));
     }
     CUDA_MEMCPY2D cp; memset(&cp, 0, sizeof(cp));
     cp.srcMemoryType = CU_MEMORYTYPE_ARRAY; cp.srcArray = c->surf_array; cp.dstMemoryType = CU_MEMORYTYPE_DEVICE; cp.dstDevice = c->e2e_stage[slot];
