@@ -265,8 +265,7 @@ __global__ void __launch_bounds__(1024) k_apply_uploads(const unsigned char* are
 template <typename K> static void preload(K kernel) { cudaFuncAttributes a; cudaFuncGetAttributes(&a, kernel); }
 static void preload_kernels() {
     preload(k_generate); preload(k_begin_pass); preload(k_fold_counters); preload(k_sort); preload(k_accumulate);
-    preload(k_trace8<false, false, true>); preload(k_trace8<true, false, true>); preload(k_trace8<false, true, true>); preload(k_trace8<true, true, true>);
-    preload(k_trace8<false, false, false>); preload(k_trace8<true, false, false>); preload(k_trace8<false, true, false>); preload(k_trace8<true, true, false>);
+    preload(k_trace8<false, false>); preload(k_trace8<true, false>); preload(k_trace8<false, true>); preload(k_trace8<true, true>);
     preload(k_trace2<false, false>); preload(k_trace2<true, false>); preload(k_trace2<false, true>); preload(k_trace2<true, true>);
     preload(k_shade<BSDFDiffuse>); preload(k_shade<BSDFPlastic>); preload(k_shade<BSDFDielectric>); preload(k_shade<BSDFConductor>);
     preload(k_bin_count<false>); preload(k_bin_count<true>); preload(k_bin_scatter<false>); preload(k_bin_scatter<true>);
@@ -294,7 +293,6 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     CKC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     if (const char* v = getenv("PTB_TRACE_OVERLAP")) ctx->overlap_enabled = atoi(v) != 0;     // A/B switch for tools/, default on
-    if (const char* v = getenv("PTB_HALF_NODES")) ctx->half_nodes = atoi(v) != 0;
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
@@ -325,14 +323,10 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     { int fe = allocate_film(ctx); if (fe) { ptb_destroy(ctx); return fe; } }
 
     preload_kernels();
-    CKC(cudaFuncSetAttribute(k_trace8<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CKC(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return 0;
@@ -755,22 +749,24 @@ static int apply_roots(ptb_ctx* ctx, const int32_t* roots, int mesh_count) {
     if (ctx->merge_slot_root.empty() && identity_roots_sorted(ctx->host_roots) == ctx->merge_decided_roots) {
         std::vector<int> r = ctx->host_roots; upload_roots(ctx, r); return 0;
     }
-    bool same = ctx->merge_enabled && ident.size() == ctx->merge_slot_root.size();
+    // Match the merged slots with the identity instances of the new table (TLAS leaf order may have changed).  A slot whose instance
+    // is gone or no longer has an identity transform is RETIRED: its slot -> instance entry becomes -1, which the triangle tests
+    // check before accepting a hit, and the instance is traced through the TLAS like any moving one.  No rebuild, no stream
+    // synchronise (the round-1 code re-merged all 262 K triangles on the CPU, 0.65 s, whenever an identity instance started moving).
+    // Instances that become identity later are simply not merged until ptb_set_static_merge() is called again.
+    if (!ctx->merge_enabled) { ctx->merge_decided_roots = identity_roots_sorted(ctx->host_roots); std::vector<int> r = ctx->host_roots; upload_roots(ctx, r); return 0; }
     std::vector<int> slot_instance(ctx->merge_slot_root.size(), -1);
-    if (same) {
-        std::vector<char> taken(ident.size(), 0);
-        for (size_t k = 0; k < slot_instance.size() && same; k++) {
-            size_t j = k < ident.size() && !taken[k] && roots[ident[k]] == ctx->merge_slot_root[k] ? k : 0;    // common case: order unchanged
-            if (!(j == k && roots[ident[j]] == ctx->merge_slot_root[k] && !taken[j]))
-                for (j = 0; j < ident.size(); j++) if (!taken[j] && roots[ident[j]] == ctx->merge_slot_root[k]) break;
-            if (j == ident.size()) { same = false; break; }
-            taken[j] = 1; slot_instance[k] = ident[j];
-        }
+    std::vector<char> taken(ident.size(), 0);
+    for (size_t k = 0; k < slot_instance.size(); k++) {
+        if (ctx->merge_slot_instance[k] < 0) continue;                                               // retired earlier: stays retired
+        size_t j = k < ident.size() && !taken[k] && roots[ident[k]] == ctx->merge_slot_root[k] ? k : ident.size();     // common case: order unchanged
+        if (j == ident.size()) for (j = 0; j < ident.size(); j++) if (!taken[j] && roots[ident[j]] == ctx->merge_slot_root[k]) break;
+        if (j == ident.size()) continue;                                                             // retire
+        taken[j] = 1; slot_instance[k] = ident[j];
     }
-    if (!same) return rebuild_static_merge(ctx);
     ctx->merge_slot_instance = slot_instance;
     std::vector<int> device_roots = ctx->host_roots;
-    for (int i : slot_instance) device_roots[i] = int((unsigned)device_roots[i] | PTB_ROOT_MERGED);
+    for (int i : slot_instance) if (i >= 0) device_roots[i] = int((unsigned)device_roots[i] | PTB_ROOT_MERGED);
     upload_roots(ctx, device_roots);
     return upload_pruned_tlas(ctx);
 }
@@ -943,15 +939,10 @@ struct StageTimer {
 
 static size_t trace8_smem() { return 16 + (size_t)PTB_TLAS_STAGE_MAX_NODES * 80 + (size_t)PTB_SM_STACK * PTB_TRACE_BLOCK * sizeof(uint2); }
 
-// which node test a launch uses: the float one whenever bit parity is promised (static merge off = the reference's two-level walk),
-// the conservative packed-half one otherwise (if built in: PTB_NODE_HALF)
 template <bool SHADOW>
 static void launch_trace8(ptb_ctx* ctx, const Frame& F, int grid, cudaStream_t st, int bounce, const unsigned* order) {
-    const bool exact = !(PTB_NODE_HALF && ctx->merge_enabled && ctx->half_nodes);
-    if (exact) { if (ctx->stats_mode) k_trace8<SHADOW, true, true><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order);
-                 else                 k_trace8<SHADOW, false, true><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order); }
-    else       { if (ctx->stats_mode) k_trace8<SHADOW, true, false><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order);
-                 else                 k_trace8<SHADOW, false, false><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order); }
+    if (ctx->stats_mode) k_trace8<SHADOW, true><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order);
+    else                 k_trace8<SHADOW, false><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order);
 }
 
 // One wave: `samples` consecutive passes (first_sample ...) through the whole pipeline.  The role of one or several

@@ -1,7 +1,6 @@
 // Device-side building blocks shared by the kernels: RNG, camera, triangle tests, CWBVH node test,
 // light sampling, microfacet helpers.  Formulas follow the reference files cited per function.
 #pragma once
-#include <cuda_fp16.h>
 #include "ptb_math.cuh"
 #include "ptb_types.cuh"
 
@@ -169,7 +168,9 @@ PTB_DI void intersect_triangle(const Frame& P, int mesh_id, int tri_id, const Ra
         float t, u, v;
         if (woop_test(P, tri_id, ray, hit.t, t, u, v)) {
             int2 who = __ldg(P.flat_who + tri_id);
-            hit.t = t; hit.u = u; hit.v = v; hit.mesh_id = -(2 + who.y); hit.triangle_id = who.x;
+            if (__ldg(P.flat_slot_instance + who.y) >= 0) {       // slot retired: its instance moved out of the merged tree (ptb_update_instances)
+                hit.t = t; hit.u = u; hit.v = v; hit.mesh_id = -(2 + who.y); hit.triangle_id = who.x;
+            }
         }
         return;
     }
@@ -185,15 +186,22 @@ PTB_DI void intersect_triangle(const Frame& P, int mesh_id, int tri_id, const Ra
         float v = f * dot(ray.d, q);
         if (v >= 0.0f && u + v <= 1.0f) {
             float t = f * dot(tr.e2, q);
-            if (t > 0.0f && t < hit.t) { hit.t = t; hit.u = u; hit.v = v; hit.mesh_id = mesh_id; hit.triangle_id = tri_id; }
+            if (t > 0.0f && t < hit.t) {
+                // merged tree: a slot whose instance has since started moving is retired, its triangles no longer count
+                if (!flat || __ldg(P.flat_slot_instance + __float_as_int(c.z)) >= 0) { hit.t = t; hit.u = u; hit.v = v; hit.mesh_id = mesh_id; hit.triangle_id = tri_id; }
+            }
         }
     }
 }
 // any hit (Triangle.h:176-198)
 PTB_DI bool occludes_triangle(const Frame& P, int mesh_id, int tri_id, const Ray& ray, float max_distance) {
     float4 c;
-    if (mesh_id == PTB_FLAT_MESH && P.flat_woop) { float t, u, v; return woop_test(P, tri_id, ray, max_distance, t, u, v); }
-    TriPos tr = mesh_id == PTB_FLAT_MESH ? load_tri_pos_flat(P, tri_id, c) : load_tri_pos(P, tri_id);
+    const bool flat = mesh_id == PTB_FLAT_MESH;
+    if (flat && P.flat_woop) {
+        float t, u, v;
+        return woop_test(P, tri_id, ray, max_distance, t, u, v) && __ldg(P.flat_slot_instance + __ldg(P.flat_who + tri_id).y) >= 0;
+    }
+    TriPos tr = flat ? load_tri_pos_flat(P, tri_id, c) : load_tri_pos(P, tri_id);
     float3 h = cross(ray.d, tr.e2);
     float a = dot(tr.e1, h);
     float f = 1.0f / a;
@@ -204,7 +212,7 @@ PTB_DI bool occludes_triangle(const Frame& P, int mesh_id, int tri_id, const Ray
         float v = f * dot(ray.d, q);
         if (v >= 0.0f && u + v <= 1.0f) {
             float t = f * dot(tr.e2, q);
-            if (t > 0.0f && t < max_distance) return true;
+            if (t > 0.0f && t < max_distance) return !flat || __ldg(P.flat_slot_instance + __float_as_int(c.z)) >= 0;
         }
     }
     return false;
@@ -259,81 +267,6 @@ PTB_DI unsigned cwbvh_node_intersect(const Ray& ray, unsigned oct_inv4, float ma
             float tmin = imax3(tmin3.x, tmin3.y, fmaxf(tmin3.z, 0.0f));
             float tmax = imin3(tmax3.x, tmax3.y, fminf(tmax3.z, max_distance));
             if (tmin < tmax) hit_mask |= byte_of(child_bits4, j) << byte_of(bit_index4, j);
-        }
-    }
-    return hit_mask;
-}
-
-// Conservative node test in packed half precision: two children per instruction.
-//
-// The float test above costs 48 byte->float conversions + 48 FFMA per node and is what the kernel spends its time on (ncu source
-// page: 47 % of the executed instructions of a bounce-1 launch).  Here the six quantised bounds of TWO children are turned into
-// half2 by one PRMT (0x6400 | byte = 1024 + byte, exact) + one HSUB2, then one HFMA2 / HMNMX2 per pair; XU-pipe conversions disappear.
-// fp16 has 11 significant bits, so the test is made CONSERVATIVE instead of exact -- it accepts every child the float test accepts
-// (tools/cpu_half_nodetest.py replays the arithmetic bit-exactly on real traversals of the merged Sponza tree: 0 of 114 K accepted
-// children rejected, 3.2 % accepted in addition):
-//   * time is measured from t0 = the ray's entry into the node's quantisation frame, so every operand is bounded by the node's own
-//     extent along the ray (|org_a - t0| <= 255 |inv_a| when the ray hits the node) instead of by the distance from the ray origin;
-//   * per axis the near planes use org - m, the far planes org + m with m = 2^-10 (|org_a - t0| + 255 |inv_a|): the rounding of
-//     inv (2^-11 relative), of the addend and of the fused result (2^-11 each) are all covered, cf. the derivation in DESIGN.md;
-//   * an axis whose operands leave the half range (ray almost parallel to the slab) is not tested at all;
-//   * the upper clamp hit.t - t0 is rounded up, the lower clamp 0 - t0 down; the final comparison is <=.
-// Used by the default traversal mode only; ptb_set_static_merge(0) (bit-exact mode) keeps the float test.
-PTB_DI __half2 bytes_to_half2(unsigned word, unsigned sel) {
-    unsigned bits = __byte_perm(word, 0x64646464u, sel);            // {0x64, b_hi, 0x64, b_lo} = (1024 + b_lo, 1024 + b_hi)
-    return __hsub2(*reinterpret_cast<__half2*>(&bits), __float2half2_rn(1024.0f));
-}
-PTB_DI unsigned cwbvh_node_intersect_half(const Ray& ray, unsigned oct_inv4, float max_distance, float4 n0, float4 n1, float4 n2, float4 n3, float4 n4) {
-    unsigned e_imask = __float_as_uint(n0.w);
-    const float idx = 1.0f / ray.d.x, idy = 1.0f / ray.d.y, idz = 1.0f / ray.d.z;
-    float inv[3] = { __uint_as_float(byte_of(e_imask, 0) << 23) * idx, __uint_as_float(byte_of(e_imask, 1) << 23) * idy, __uint_as_float(byte_of(e_imask, 2) << 23) * idz };
-    float org[3] = { (n0.x - ray.o.x) * idx, (n0.y - ray.o.y) * idy, (n0.z - ray.o.z) * idz };
-    const bool neg[3] = { ray.d.x < 0.0f, ray.d.y < 0.0f, ray.d.z < 0.0f };
-    float t0 = 0.0f;
-#pragma unroll
-    for (int a = 0; a < 3; a++) t0 = fmaxf(t0, neg[a] ? fmaf(255.0f, inv[a], org[a]) : org[a]);     // fmaxf drops NaN operands
-    t0 = fminf(t0, 1e30f);
-    __half2 inv2[3], lo2[3], hi2[3];
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-        float os = org[a] - t0;
-        float reach = fabsf(os) + 255.0f * fabsf(inv[a]);
-        float m = reach * (1.0f / 1024.0f);
-        bool ok = reach <= 30000.0f;                                   // false for NaN too
-        inv2[a] = __float2half2_rn(ok ? inv[a] : 0.0f);
-        lo2[a] = __float2half2_rn(ok ? os - m : -60000.0f);
-        hi2[a] = __float2half2_rn(ok ? os + m : 60000.0f);
-    }
-    const __half2 zero2 = __float2half2_rn(-t0 * (1.0f + 1.0f / 512.0f));                            // <= 0 - t0  (t0 >= 0)
-    float th = max_distance - t0;
-    th = fminf(th + fabsf(th) * (1.0f / 256.0f) + 1e-6f, 65504.0f);                                   // >= hit.t - t0; +inf -> largest half
-    const __half2 thit2 = __float2half2_rn(th != th ? 65504.0f : th);
-    unsigned hit_mask = 0;
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        unsigned meta4 = __float_as_uint(i == 0 ? n1.z : n1.w);
-        unsigned is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        unsigned inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-        unsigned bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-        unsigned child_bits4 = (meta4 >> 5) & 0x07070707u;
-        unsigned qlx = __float_as_uint(i == 0 ? n2.x : n2.y), qhx = __float_as_uint(i == 0 ? n2.z : n2.w);
-        unsigned qly = __float_as_uint(i == 0 ? n3.x : n3.y), qhy = __float_as_uint(i == 0 ? n3.z : n3.w);
-        unsigned qlz = __float_as_uint(i == 0 ? n4.x : n4.y), qhz = __float_as_uint(i == 0 ? n4.z : n4.w);
-        unsigned x_min = neg[0] ? qhx : qlx, x_max = neg[0] ? qlx : qhx;
-        unsigned y_min = neg[1] ? qhy : qly, y_max = neg[1] ? qly : qhy;
-        unsigned z_min = neg[2] ? qhz : qlz, z_max = neg[2] ? qlz : qhz;
-#pragma unroll
-        for (int j = 0; j < 4; j += 2) {
-            const unsigned sel = j == 0 ? 0x4140u : 0x4342u;
-            __half2 tnx = __hfma2(bytes_to_half2(x_min, sel), inv2[0], lo2[0]), tfx = __hfma2(bytes_to_half2(x_max, sel), inv2[0], hi2[0]);
-            __half2 tny = __hfma2(bytes_to_half2(y_min, sel), inv2[1], lo2[1]), tfy = __hfma2(bytes_to_half2(y_max, sel), inv2[1], hi2[1]);
-            __half2 tnz = __hfma2(bytes_to_half2(z_min, sel), inv2[2], lo2[2]), tfz = __hfma2(bytes_to_half2(z_max, sel), inv2[2], hi2[2]);
-            __half2 tmin2 = __hmax2(__hmax2(tnx, tny), __hmax2(tnz, zero2));
-            __half2 tmax2 = __hmin2(__hmin2(tfx, tfy), __hmin2(tfz, thit2));
-            __half2 le = __hle2(tmin2, tmax2);                       // 1.0 (0x3c00) per lane where tmin <= tmax
-            unsigned bits = *reinterpret_cast<unsigned*>(&le);
-            if (bits & 0x0000ffffu) hit_mask |= byte_of(child_bits4, j) << byte_of(bit_index4, j);
-            if (bits & 0xffff0000u) hit_mask |= byte_of(child_bits4, j + 1) << byte_of(bit_index4, j + 1);
         }
     }
     return hit_mask;

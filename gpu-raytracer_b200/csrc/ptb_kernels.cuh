@@ -29,9 +29,6 @@
 #ifndef PTB_SHADE_MIN_BLOCKS_DIFFUSE
 #define PTB_SHADE_MIN_BLOCKS_DIFFUSE 4    // 64 registers (120 B of spills) but twice the gathers in flight: frame 32.72 -> 32.21 ms
 #endif
-#ifndef PTB_NODE_HALF
-#define PTB_NODE_HALF 0                   // (1:) default traversal mode uses the conservative packed-half node test
-#endif
 #ifndef PTB_TILED_GENERATE
 #define PTB_TILED_GENERATE 1              // primary rays enumerated so that a warp covers an 8x4 pixel tile (not a 32x1 strip)
 #endif
@@ -191,8 +188,7 @@ PTB_DI uint2 stack_pop(const TraceShared& S, const uint2* local, int& sp) {
 
 // STATS = true additionally counts node visits / triangle tests / instance transforms per ray kind (roofline accounting:
 // algorithmic bytes = 80 B per node + 48 B per triangle + 48 B per instance transform + the ray/hit streams).
-// EXACT = true: the reference's float node test (bit-exact mode); false: the conservative packed-half test (ptb_device.cuh).
-template <bool SHADOW, bool STATS, bool EXACT>
+template <bool SHADOW, bool STATS>
 __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace8(const __grid_constant__ Frame P, int bounce, const unsigned* __restrict__ order) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -292,7 +288,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                         n0 = __ldg(n); n1 = __ldg(n + 1); n2 = __ldg(n + 2); n3 = __ldg(n + 3); n4 = __ldg(n + 4);
                     }
                     if (STATS) st_nodes++;
-                    unsigned hm = EXACT ? cwbvh_node_intersect(ray, oct4, hit.t, n0, n1, n2, n3, n4) : cwbvh_node_intersect_half(ray, oct4, hit.t, n0, n1, n2, n3, n4);
+                    unsigned hm = cwbvh_node_intersect(ray, oct4, hit.t, n0, n1, n2, n3, n4);
                     unsigned imask = byte_of(__float_as_uint(n0.w), 3);
                     cur.x = __float_as_uint(n1.x);
                     tri.x = __float_as_uint(n1.y);

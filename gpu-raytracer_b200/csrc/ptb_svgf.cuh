@@ -69,8 +69,11 @@ __global__ void __launch_bounds__(256) k_svgf_reproject(const __grid_constant__ 
         float4 moment;
         moment.x = luminance(direct.x, direct.y, direct.z);
         moment.y = luminance(indirect.x, indirect.y, indirect.z);
-        moment.z = moment.x * moment.x;
-        moment.w = moment.y * moment.y;
+        // the squares are rounded products of their own (mul.rn): left as plain `x * x`, ptxas folds them into the subtraction of the
+        // moment lerp below (FFMA), which the reference build does not do -- its squares have a second use -- and every frame after
+        // the first differed from the reference in the last bit of the second moments (tools/gpu_svgf_diag.py)
+        moment.z = __fmul_rn(moment.x, moment.x);
+        moment.w = __fmul_rn(moment.y, moment.y);
         float4 nd = P.svgf.in_normal_depth[px];
         float2 sprev = P.svgf.in_screen_prev[px];
         float3 normal = oct_decode_normal(f2(nd.x, nd.y));

@@ -238,7 +238,8 @@ def test_static_merge_is_invisible(big):
 
 def test_static_merge_follows_instance_updates():
     """ptb_update_instances re-sending the same tables (per-frame fast path) and with an identity instance turning into a
-    moving one (the merged BVH is rebuilt without it): the image stays equal to the un-merged one."""
+    moving one (its slot in the merged BVH is retired -- no rebuild, no stall -- and the instance is traced through the TLAS
+    again): the image stays equal to the un-merged one."""
     import ctypes
     d = scene.procedural_scene("soup", seed=4, width=256, height=160, detail=0.5)
     blob = scene.build_blob(d, 8, rng="fallback")
