@@ -34,8 +34,20 @@ def report(tag, a, b):
     for k in range(min(3, n)):
         print(f"        ({xs[k]},{ys[k]}) ours {a[ys[k], xs[k]]} ref {b[ys[k], xs[k]]}")
 
+mode = os.environ.get("DIAG_MODE", "sync")         # "sync": compare after every frame; "nosync": queue all frames, compare the last;
+extra = None                                       # "third": nosync + a second ptb context rendering alongside (what the pytest case does)
+if mode == "third":
+    extra = pt.Pathtracer(blob, config=cfg)
 for si in range(frames):
-    p.render_pass(si); r.render_pass(si); p.sync(); r.sync()
+    if mode == "sync":
+        p.render_pass(si); r.render_pass(si); p.sync(); r.sync()
+    else:
+        r.render_pass(si); p.render_pass(si)
+        if extra is not None:
+            extra.render_pass(si)
+        if si != frames - 1:
+            continue
+        p.sync(); r.sync()
     print(f"frame {si}")
     report("display", p.get_display(), r.get_display())
     for k, nm in ((1, "acc_direct"), (2, "acc_indirect")):
