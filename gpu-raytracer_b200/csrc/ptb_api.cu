@@ -97,11 +97,6 @@ struct ptb_ctx {
     // side stream so that the tail of one persistent trace kernel is filled by the CTAs of the other (render_wave)
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    // second lane (ptb_set_wave_lanes(ctx, 2)): the other half of a frame's passes runs concurrently on these
-    int wave_lanes = 1;
-    cudaStream_t stream2 = nullptr, side_stream2 = nullptr;
-    cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr, ev_split = nullptr, ev_lane_done = nullptr;
-    Counters* counters2 = nullptr;
     bool overlap_enabled = true;
     // static merge: identity-transform instances re-built into ONE CWBVH at upload (rebuild_static_merge)
     bool merge_enabled = true;
@@ -344,9 +339,6 @@ extern "C" void ptb_destroy(ptb_ctx* ctx) {
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
-    if (ctx->side_stream2) { cudaStreamSynchronize(ctx->side_stream2); cudaStreamDestroy(ctx->side_stream2); }
-    for (cudaEvent_t ev : { ctx->ev_fork2, ctx->ev_join2, ctx->ev_split, ctx->ev_lane_done }) if (ev) cudaEventDestroy(ev);
     for (void*& m : ctx->xchg_ipc_opened) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
     if (ctx->xchg_block) { cudaFree(ctx->xchg_block); ctx->xchg_block = nullptr; }
     for (int c = 0; c < 2; c++) { if (ctx->stage_mem[c]) cudaFreeHost(ctx->stage_mem[c]); if (ctx->stage_dev[c]) cudaFree(ctx->stage_dev[c]); if (ctx->stage_done[c]) cudaEventDestroy(ctx->stage_done[c]); }
@@ -955,62 +947,6 @@ static void launch_trace8(ptb_ctx* ctx, const Frame& F, int grid, cudaStream_t s
 
 // One wave: `samples` consecutive passes (first_sample ...) through the whole pipeline.  The role of one or several
 // Pathtracer::render() calls (Pathtracer.cpp:738-855); asynchronous, no host<->device synchronisation.
-// Streams and events of one lane.  A frame's passes can be traced as TWO concurrent half-waves (ptb_set_wave_lanes): each lane has
-// its own slice of the queues, its own counters and its own pair of streams, so the ramp-down tail of one lane's persistent trace
-// kernels is filled by the other lane's launches (what costs a rank of 8 ten percent of its frame, profiles/r1_summary.md).
-struct LaneStreams { cudaStream_t st, side; cudaEvent_t fork, join; };
-
-// generate -> per bounce { trace, sort, shade x types, shadow trace } for the passes F describes, on the lane's streams
-static int trace_lane(ptb_ctx* ctx, const Frame& F, const LaneStreams& L) {
-    cudaStream_t st = L.st;
-    const int g1d = grid_for(ctx, 8);
-    const int gtrace = grid_for(ctx, PTB_TRACE_MIN_BLOCKS);
-    const bool nee = ctx->has_lights && F.config.enable_next_event_estimation;
-
-    k_begin_pass<<<1, 256, 0, st>>>(F); ctx->launches++;
-    { StageTimer t(ctx, ST_GENERATE); k_generate<<<g1d, 256, 0, st>>>(F); ctx->launches++; }
-    // Dependencies inside a bounce: trace -> sort -> shade -> { shadow trace, next bounce's trace }.  The two traces only meet
-    // again at the next sort (both deposit into the framebuffer: shadow first, to keep the reference's summation order), so the
-    // shadow trace runs on a side stream; its CTAs and the next closest-hit trace's CTAs fill each other's ramp-down tails.
-    // Per-stage timing (events on the main stream) and the ordering experiment keep everything on one stream.
-    const bool overlap = ctx->overlap_enabled && nee && !ctx->timing && !ctx->stats_mode && F.order_bins == 0;
-    bool side_pending = false;
-    for (int bounce = 0; bounce < F.config.num_bounces; bounce++) {
-        const bool ordered = F.order_bins > 0 && ctx->bvh_kind == 8 && bounce < PTB_ORDER_MAX_BOUNCE;
-        const unsigned* order_c = ordered && bounce > 0 ? F.order : nullptr;       // primary rays are coherent as generated
-        const unsigned* order_s = ordered ? F.order : nullptr;
-        if (order_c) { StageTimer t(ctx, ST_ORDER);
-          k_bin_count<false><<<g1d, 256, 0, st>>>(F, bounce); k_bin_scatter<false><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches += 2; }
-        { StageTimer t(ctx, ST_TRACE);
-          if (ctx->bvh_kind == 8) { launch_trace8<false>(ctx, F, gtrace, st, bounce, order_c); }
-          else if (ctx->stats_mode) k_trace2<false, true><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
-          else                    k_trace2<false, false><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
-          ctx->launches++; }
-        if (side_pending) { CK(cudaStreamWaitEvent(st, L.join, 0)); side_pending = false; }     // shadow[bounce-1] deposits before sort[bounce]
-        { StageTimer t(ctx, ST_SORT); k_sort<<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
-        { StageTimer t(ctx, ST_SHADE);
-          if (ctx->has_type[0]) { k_shade<BSDFDiffuse><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
-          if (ctx->has_type[1]) { k_shade<BSDFPlastic><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
-          if (ctx->has_type[2]) { k_shade<BSDFDielectric><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
-          if (ctx->has_type[3]) { k_shade<BSDFConductor><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; } }
-        if (nee && order_s) { StageTimer t(ctx, ST_ORDER);
-          k_bin_count<true><<<g1d, 256, 0, st>>>(F, bounce); k_bin_scatter<true><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches += 2; }
-        if (nee) {
-            StageTimer t(ctx, ST_SHADOW);
-            cudaStream_t ss = st;
-            if (overlap) { CK(cudaEventRecord(L.fork, st)); CK(cudaStreamWaitEvent(L.side, L.fork, 0)); ss = L.side; }
-            if (ctx->bvh_kind == 8) { launch_trace8<true>(ctx, F, gtrace, ss, bounce, order_s); }
-            else if (ctx->stats_mode) k_trace2<true, true><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce);
-            else                    k_trace2<true, false><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce);
-            ctx->launches++;
-            if (overlap) { CK(cudaEventRecord(L.join, L.side)); side_pending = true; }
-        }
-    }
-    if (side_pending) { CK(cudaStreamWaitEvent(st, L.join, 0)); side_pending = false; }
-    k_fold_counters<<<1, PTB_MAX_BOUNCES, 0, st>>>(F); ctx->launches++;
-    return 0;
-}
-
 static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = false) {
     if (samples < 1 || samples > ctx->wave_capacity) return PTB_E_BADARG;
     Frame F = ctx->F;
@@ -1048,28 +984,49 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
     if (F.config.enable_svgf && samples != 1) return PTB_E_STATE;   // SVGF is temporal: one pass per displayed frame
     cudaStream_t st = ctx->stream;
     const int g1d = grid_for(ctx, 8);
-    const LaneStreams lane0 = { ctx->stream, ctx->side_stream, ctx->ev_fork, ctx->ev_join };
-    const bool split = ctx->wave_lanes == 2 && samples >= 2 && !F.config.enable_svgf && !ctx->timing && !ctx->stats_mode && F.order_bins == 0 && ctx->stream2;
-    if (!split) {
-        int e = trace_lane(ctx, F, lane0); if (e) return e;
-    } else {
-        // two half-waves: slots [0, s0) on lane 0, [s0, samples) on lane 1; each slot still deposits into its own framebuffer plane,
-        // so the fold in k_accumulate -- and the image -- is the same as for one wave
-        const int s0 = (samples + 1) / 2, s1 = samples - s0;
-        Frame F0 = F, F1 = F;
-        F0.wave_samples = s0;
-        F1.wave_samples = s1; F1.first_sample = first_sample + s0; F1.slot_base = s0;
-        const size_t off = (size_t)F.local_pixels * s0;
-        for (int i = 0; i < 2; i++) { F1.q[i].od0 += off; F1.q[i].od1 += off; F1.q[i].hit += off; F1.q[i].path += off; F1.q[i].pix += off; F1.q[i].medium += off; }
-        F1.sq.od0 += off; F1.sq.od1 += off; F1.sq.illum += off;
-        for (int m = 0; m < 4; m++) F1.matq[m] += off;
-        F1.counters = ctx->counters2;
-        const LaneStreams lane1 = { ctx->stream2, ctx->side_stream2, ctx->ev_fork2, ctx->ev_join2 };
-        CK(cudaEventRecord(ctx->ev_split, st)); CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_split, 0));
-        int e = trace_lane(ctx, F0, lane0); if (e) return e;
-        e = trace_lane(ctx, F1, lane1); if (e) return e;
-        CK(cudaEventRecord(ctx->ev_lane_done, ctx->stream2)); CK(cudaStreamWaitEvent(st, ctx->ev_lane_done, 0));
+    const int gtrace = grid_for(ctx, PTB_TRACE_MIN_BLOCKS);
+    const bool nee = ctx->has_lights && F.config.enable_next_event_estimation;
+
+    k_begin_pass<<<1, 256, 0, st>>>(F); ctx->launches++;
+    { StageTimer t(ctx, ST_GENERATE); k_generate<<<g1d, 256, 0, st>>>(F); ctx->launches++; }
+    // Dependencies inside a bounce: trace -> sort -> shade -> { shadow trace, next bounce's trace }.  The two traces only meet
+    // again at the next sort (both deposit into the framebuffer: shadow first, to keep the reference's summation order), so the
+    // shadow trace runs on a side stream; its CTAs and the next closest-hit trace's CTAs fill each other's ramp-down tails.
+    // Per-stage timing (events on the main stream) and the ordering experiment keep everything on one stream.
+    const bool overlap = ctx->overlap_enabled && nee && !ctx->timing && !ctx->stats_mode && F.order_bins == 0;
+    bool side_pending = false;
+    for (int bounce = 0; bounce < F.config.num_bounces; bounce++) {
+        const bool ordered = F.order_bins > 0 && ctx->bvh_kind == 8 && bounce < PTB_ORDER_MAX_BOUNCE;
+        const unsigned* order_c = ordered && bounce > 0 ? F.order : nullptr;       // primary rays are coherent as generated
+        const unsigned* order_s = ordered ? F.order : nullptr;
+        if (order_c) { StageTimer t(ctx, ST_ORDER);
+          k_bin_count<false><<<g1d, 256, 0, st>>>(F, bounce); k_bin_scatter<false><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches += 2; }
+        { StageTimer t(ctx, ST_TRACE);
+          if (ctx->bvh_kind == 8) { launch_trace8<false>(ctx, F, gtrace, st, bounce, order_c); }
+          else if (ctx->stats_mode) k_trace2<false, true><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
+          else                    k_trace2<false, false><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
+          ctx->launches++; }
+        if (side_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); side_pending = false; }     // shadow[bounce-1] deposits before sort[bounce]
+        { StageTimer t(ctx, ST_SORT); k_sort<<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
+        { StageTimer t(ctx, ST_SHADE);
+          if (ctx->has_type[0]) { k_shade<BSDFDiffuse><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
+          if (ctx->has_type[1]) { k_shade<BSDFPlastic><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
+          if (ctx->has_type[2]) { k_shade<BSDFDielectric><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
+          if (ctx->has_type[3]) { k_shade<BSDFConductor><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; } }
+        if (nee && order_s) { StageTimer t(ctx, ST_ORDER);
+          k_bin_count<true><<<g1d, 256, 0, st>>>(F, bounce); k_bin_scatter<true><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches += 2; }
+        if (nee) {
+            StageTimer t(ctx, ST_SHADOW);
+            cudaStream_t ss = st;
+            if (overlap) { CK(cudaEventRecord(ctx->ev_fork, st)); CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0)); ss = ctx->side_stream; }
+            if (ctx->bvh_kind == 8) { launch_trace8<true>(ctx, F, gtrace, ss, bounce, order_s); }
+            else if (ctx->stats_mode) k_trace2<true, true><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce);
+            else                    k_trace2<true, false><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce);
+            ctx->launches++;
+            if (overlap) { CK(cudaEventRecord(ctx->ev_join, ctx->side_stream)); side_pending = true; }
+        }
     }
+    if (side_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); side_pending = false; }
     { StageTimer t(ctx, ST_POST);
       if (F.config.enable_svgf) {
           int e = launch_svgf(F, st, first_sample, g1d, &ctx->launches); if (e) return e;
@@ -1078,6 +1035,7 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
           k_accumulate<<<g1d, 256, 0, st>>>(F); ctx->launches++;
           if (F.xchg.push) { k_exchange_wait<<<1, 1, 0, st>>>(F); ctx->launches++; }
       } }
+    k_fold_counters<<<1, PTB_MAX_BOUNCES, 0, st>>>(F); ctx->launches++;
     if (!ctx->capturing) CK(cudaGetLastError());
     ctx->last_sample_index = first_sample + samples - 1;
     ctx->frames_since_reset += samples;
@@ -1090,24 +1048,6 @@ extern "C" int ptb_render(ptb_ctx* ctx, int sample_index) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->timing) { ctx->timed.clear(); ctx->event_used = 0; }
     return render_wave(ctx, sample_index, 1);
-}
-
-extern "C" int ptb_set_wave_lanes(ptb_ctx* ctx, int lanes) {
-    if (!ctx || (lanes != 1 && lanes != 2)) return PTB_E_BADARG;
-    CK(cudaSetDevice(ctx->device));
-    if (lanes == ctx->wave_lanes) return 0;
-    drop_graphs(ctx);
-    if (lanes == 2 && !ctx->stream2) {
-        CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&ctx->side_stream2, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ctx->ev_split, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_lane_done, cudaEventDisableTiming));
-        if (dev_alloc(ctx, &ctx->counters2, 1)) return PTB_E_STATE;
-        CK(cudaMemsetAsync(ctx->counters2, 0, sizeof(Counters), ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    ctx->wave_lanes = lanes;
-    return 0;
 }
 
 extern "C" int ptb_set_ray_ordering(ptb_ctx* ctx, int bins) {

@@ -275,7 +275,7 @@ PTB_DI unsigned cwbvh_node_intersect(const Ray& ray, unsigned oct_inv4, float ma
 // ------------------------------------------------------------------------------------------ pixel word: pixel | slot << pix_bits | flags
 PTB_DI int word_pixel(const Frame& P, unsigned w) { return int(w & ((1u << P.pix_bits) - 1u)); }
 PTB_DI int word_slot(const Frame& P, unsigned w) { return int((w & ~PTB_FLAGS_ALL) >> P.pix_bits); }
-PTB_DI int word_fb_index(const Frame& P, unsigned w) { return (word_slot(P, w) + P.slot_base) * P.fb_stride + word_pixel(P, w); }
+PTB_DI int word_fb_index(const Frame& P, unsigned w) { return word_slot(P, w) * P.fb_stride + word_pixel(P, w); }
 
 // ------------------------------------------------------------------------------------------ AOV helpers (AOV.h:4-46); px = framebuffer index (slot plane + pixel)
 PTB_DI void aov_set(const Frame& P, int k, int px, float4 v) { if (P.aov[k].fb) P.aov[k].fb[px] = v; }

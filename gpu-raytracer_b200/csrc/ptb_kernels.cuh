@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, i
                 ended = true;
             }
             if (!ended) {
-                if (bounce == 0 && P.pixel_query[0] == pixel_index && word_slot(P, pf) + P.slot_base == 0) {     // GUI picking (Pathtracer.cu:345-348); pixel_index is -1 unless a query is pending
+                if (bounce == 0 && P.pixel_query[0] == pixel_index && word_slot(P, pf) == 0) {     // GUI picking (Pathtracer.cu:345-348); pixel_index is -1 unless a query is pending
                     P.pixel_query[1] = hit.mesh_id; P.pixel_query[2] = hit.triangle_id;
                 }
                 int material_id = P.mesh_material_ids[hit.mesh_id];
@@ -1224,11 +1224,11 @@ __global__ void k_begin_pass(const __grid_constant__ Frame P) {
 __global__ void k_fold_counters(const __grid_constant__ Frame P) {
     int b = threadIdx.x;
     if (b < PTB_MAX_BOUNCES) {
-        if (P.counters->trace[b]) atomicAdd(&P.totals->trace[b], (unsigned long long)P.counters->trace[b]);      // two lanes may fold at once
-        if (P.counters->shadow[b]) atomicAdd(&P.totals->shadow[b], (unsigned long long)P.counters->shadow[b]);
+        P.totals->trace[b] += (unsigned long long)P.counters->trace[b];
+        P.totals->shadow[b] += (unsigned long long)P.counters->shadow[b];
         for (int m = 0; m < 4; m++) if (P.counters->mat[m][b]) atomicAdd(&P.totals->mat[m], (unsigned long long)P.counters->mat[m][b]);
     }
-    if (b == 0 && P.slot_base == 0) P.totals->frames += 1ull;
+    if (b == 0) P.totals->frames += 1ull;
 }
 
 // primary-hit tap for parity tests: pixel-keyed copy of the bounce-0 hits

@@ -165,7 +165,6 @@ struct Frame {
     // framebuffer plane, and k_accumulate folds the planes into the running mean in pass order, so the result is bit-identical
     // to tracing the passes one after another.
     int wave_samples, first_sample;
-    int slot_base;                    // framebuffer plane of this launch's slot 0 (second lane of a split frame: ptb_set_wave_lanes)
     int pix_bits;                     // pixel index occupies the low pix_bits of the `pix` word, the pass slot the bits above (below the 2 flag bits)
     int fb_stride;                    // pitch * height: distance between framebuffer planes of consecutive slots
     ptb_config config;

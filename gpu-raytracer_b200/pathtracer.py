@@ -68,7 +68,7 @@ class PtbTraversalStats(ctypes.Structure):
 
 
 # every symbol include/ptb.h declares (tests check the built library exports exactly these)
-ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_reserve_wave", "ptb_set_wave_lanes", "ptb_set_ray_ordering", "ptb_set_static_merge", "ptb_set_intersector", "ptb_resize", "ptb_render_frame",
+ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_reserve_wave", "ptb_set_ray_ordering", "ptb_set_static_merge", "ptb_set_intersector", "ptb_resize", "ptb_render_frame",
                "ptb_measure_traversal", "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_download", "ptb_get_ray_stats", "ptb_set_pixel_query", "ptb_get_pixel_query", "ptb_get_stream", "ptb_export_rows",
                "ptb_assemble_rows", "ptb_exchange_create", "ptb_exchange_connect", "ptb_exchange_connect_ipc", "ptb_exchange_frame", "ptb_exchange_disconnect", "ptb_debug_read", "ptb_launch_count", "ptb_set_timing", "ptb_get_stage_ms", "ptb_stage_name",
                "ptb_error_string"]
@@ -92,7 +92,6 @@ def lib():
         l.ptb_render.argtypes = [vp, ci]
         l.ptb_render_frame.argtypes = [vp, ci, ci]
         l.ptb_reserve_wave.argtypes = [vp, ci]
-        l.ptb_set_wave_lanes.argtypes = [vp, ci]
         l.ptb_set_ray_ordering.argtypes = [vp, ci]
         l.ptb_set_static_merge.argtypes = [vp, ci]
         l.ptb_set_intersector.argtypes = [vp, ci]
@@ -253,10 +252,6 @@ class Pathtracer:
     def reserve_wave(self, samples):
         """Let a wave carry `samples` passes at once (ptb_reserve_wave); results stay bit-identical to pass-by-pass tracing."""
         _check(lib().ptb_reserve_wave(self._ctx, int(samples)), "ptb_reserve_wave")
-
-    def set_wave_lanes(self, lanes):
-        """include/ptb.h: ptb_set_wave_lanes -- 2 = trace a frame's passes as two concurrent half-waves (same image)."""
-        _check(lib().ptb_set_wave_lanes(self._ctx, int(lanes)), "ptb_set_wave_lanes")
 
     def render_frame(self, passes):
         """One displayed frame of the reference's `-N passes` mode: Integrator bookkeeping for a fresh accumulation

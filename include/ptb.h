@@ -143,10 +143,6 @@ int  ptb_render(ptb_ctx* ctx, int sample_index);
  * passes TOGETHER (every ray carries its pass slot; each slot has its own framebuffer plane; the accumulate pass folds the
  * planes in pass order, so accumulators are bit-identical to tracing pass by pass).  Re-allocates the ray queues. */
 int  ptb_reserve_wave(ptb_ctx* ctx, int samples);
-/* lanes = 2: ptb_render_frame traces the passes of a wave as two concurrent half-waves (own queue slices, counters and stream pairs);
- * the ramp-down tail of one lane's persistent trace kernels is filled by the other lane's launches.  Same image bit for bit (every
- * pass slot still has its own framebuffer plane).  Pays on small per-GPU shares (multi-GPU tile shards); default 1. */
-int  ptb_set_wave_lanes(ptb_ctx* ctx, int lanes);
 /* The reference's `-N <samples>` capture loop (Src/Main.cpp:137-142: update + render until sample_index == N):
  * `num_passes` consecutive ptb_render calls (sample_index = first_sample_index ...) replayed as ONE CUDA graph: the launch
  * sequence of a frame is static (queue sizes live in device memory), so the ~20 launches per pass cost one graph launch per

@@ -117,29 +117,6 @@ def test_multi_pass_waves_are_bit_identical_to_pass_by_pass(wave, world):
     base.close()
 
 
-@pytest.mark.parametrize("world", [1, 2])
-def test_two_wave_lanes_are_bit_identical_to_one(world):
-    """ptb_set_wave_lanes(2): the passes of a frame traced as two concurrent half-waves (own queue slices, counters, stream pairs)
-    give the same accumulator, display and ray counters as one wave -- every pass slot keeps its own framebuffer plane and the fold
-    order in k_accumulate does not change.  Odd pass count (5 + 4), graph replay, with and without tile sharding."""
-    d = scene.procedural_scene("atrium", seed=5, width=352, height=208, detail=0.5)
-    blob = scene.build_blob(d, 8, rng="fallback")
-    cfg = pt.default_config(num_bounces=4, aov_mask=0x3F)
-    outs = []
-    for lanes in (1, 2):
-        p = pt.Pathtracer(blob, rank=0, world=world, band_rows=8, config=cfg); p.reserve_wave(9); p.set_wave_lanes(lanes)
-        for _ in range(3):
-            p.render_frame(8)                      # capture + two replays
-        p.sync()
-        outs.append(([p.get_aov(k) for k in range(6)], p.get_display(), p.ray_stats()))
-        p.close()
-    for k in range(6):
-        assert np.array_equal(outs[0][0][k].view(np.uint32), outs[1][0][k].view(np.uint32)), pt.AOV_NAMES[k]
-    assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
-    assert np.array_equal(outs[0][2]["trace"], outs[1][2]["trace"]) and np.array_equal(outs[0][2]["shadow"], outs[1][2]["shadow"])
-    assert outs[0][2]["frames"] == outs[1][2]["frames"]
-
-
 def test_edge_cases():
     # width not a multiple of 32 (pitch padding), one bounce, no lights, a single triangle
     d = scene.procedural_scene("soup", seed=2, width=70, height=33, detail=0.1)

@@ -6,13 +6,11 @@ sys.path.insert(0, ROOT)
 import torch
 from gpu_raytracer_b200 import pathtracer as pt, scene
 blob = scene.load_blob(os.path.join(ROOT, "data", "_staged", "sponza.npz"))
-lanes = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-print(f"wave lanes = {lanes}")
 base = None
 for world in (1, 2, 4, 8):
     for rank in ((0,) if world < 8 else (0, 3)):
         p = pt.Pathtracer(blob, rank=rank, world=world, band_rows=8, config=pt.default_config(num_bounces=4))
-        p.reserve_wave(9); p.set_wave_lanes(lanes)
+        p.reserve_wave(9)
         for _ in range(3): p.render_frame(8)
         p.sync()
         s = torch.cuda.ExternalStream(p.stream())
