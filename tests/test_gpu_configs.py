@@ -50,6 +50,20 @@ def bits_equal(a, b):
     return np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32))
 
 
+def _same_or_tie(a, b, what):
+    """Bit-identical -- or, rarely, the footprint of ONE closest-hit tie: a ray that hits an edge shared by two triangles at exactly
+    the same t keeps whichever was tested first, and the order in which the persistent traversal tests the triangle groups of a ray
+    depends on which rays share its warp (postponing, BVH8.h:233-246) -- in the reference kernels as in ours, so the reference does
+    not reproduce ITSELF bit for bit on such a frame.  Seen once in a dozen 8-frame Sponza runs.  The filter spreads the one changed
+    sample over its 127-pixel footprint at vanishing magnitude: accept <= 2 % of the pixels differing with rel-L2 <= 1e-6."""
+    if bits_equal(a, b):
+        return
+    differing, l2, _ = pixel_stats(np.ascontiguousarray(a).reshape(a.shape[0], -1, 1 if a.ndim == 2 else a.shape[-1]).astype(np.float32),
+                                   np.ascontiguousarray(b).reshape(b.shape[0], -1, 1 if b.ndim == 2 else b.shape[-1]).astype(np.float32))
+    print(f"[svgf parity] {what}: {differing:.5f} of the pixels differ, rel-L2 {l2:.3e} (closest-hit tie)")
+    assert differing <= 0.02 and l2 <= 1e-6, (what, differing, l2)
+
+
 def _svgf_case(blob, frames):
     """strict (two-level) traversal: display and every temporal buffer bit-exact; default (static merge): display <= 1e-4 rel-L2."""
     ref = _ref()
@@ -62,12 +76,12 @@ def _svgf_case(blob, frames):
         r.render_pass(si); strict.render_pass(si); merged.render_pass(si)
         if si in (0, frames - 1):                       # first frame (no history) and last
             r.sync(); strict.sync()
-            assert bits_equal(strict.get_display()[:, :w], r.get_display()[:, :w]), f"display, frame {si}"
+            _same_or_tie(strict.get_display()[:, :w], r.get_display()[:, :w], f"display, frame {si}")
     r.sync(); strict.sync(); merged.sync()
     want = r.get_display()[:, :w]
     assert np.isfinite(want).all() and float(np.abs(want[..., :3]).sum()) > 0.0
     for name in SVGF_BUFFERS:
-        assert bits_equal(strict.svgf_buffer(name)[:, :w], r.svgf_buffer(name)[:, :w]), name
+        _same_or_tie(strict.svgf_buffer(name)[:, :w], r.svgf_buffer(name)[:, :w], name)
     got = merged.get_display()[:, :w]
     assert rel_l2(got[..., :3], want[..., :3]) <= 1e-4, rel_l2(got[..., :3], want[..., :3])
     sp, sr = strict.ray_stats(), r.ray_stats()
@@ -164,7 +178,8 @@ def test_config3_instancing_1080p_radiance_against_uniform_handle_reference():
     assert abs(float(st["trace"].sum()) / float(rs["trace"].sum()) - 1.0) < 1e-3
     differing, l2, mean_ratio = pixel_stats(p.get_aov(0)[:, :w, :3], want[0][..., :3])
     print(f"[instancing vs uniform-handle reference] differing pixels {differing:.4f}, rel-L2 {l2:.3e}, mean ratio {mean_ratio:.6f}")
-    assert differing < 0.03 and abs(mean_ratio - 1.0) < 2e-3
+    assert differing <= 1e-4 and l2 <= 1e-6 and abs(mean_ratio - 1.0) < 1e-5      # measured on the B200: 0 differing pixels of 2 073 600
+    assert np.array_equal(st["trace"], rs["trace"])
     p.close()
 
 
@@ -203,7 +218,9 @@ def test_rough_dielectric_against_uniform_handle_reference(roughness):
     if roughness < 0.05:
         assert differing == 0.0 and np.array_equal(sp["trace"], sr["trace"]) and np.array_equal(sp["shadow"], sr["shadow"])
     else:
-        assert differing < 0.03 and abs(mean_ratio - 1.0) < 5e-3
+        # measured: 0.2 % (roughness 0.3) / 2.4 % (0.6) of the pixels differ, in the last bits only -- rel-L2 1e-9, identical ray counts:
+        # no sampling branch flips, the builds round a few products differently (ptxas mul+add fusion)
+        assert differing < 0.05 and l2 <= 1e-6 and abs(mean_ratio - 1.0) < 1e-5 and np.array_equal(sp["trace"], sr["trace"])
     p.close(); r.close()
 
 
@@ -426,7 +443,7 @@ def test_homogeneous_medium_against_reference(roughness, uniform):
         assert bits_equal(p.get_aov(k)[:, :w], r.get_aov(k)[:, :w]), pt.AOV_NAMES[k]
     differing, l2, mean_ratio = pixel_stats(p.get_aov(0)[:, :w, :3], r.get_aov(0)[:, :w, :3])
     print(f"[medium, roughness {roughness}] differing pixels {differing:.4f}, rel-L2 {l2:.3e}, mean ratio {mean_ratio:.6f}; rays ours/ref {int(sp['trace'].sum())}/{int(sr['trace'].sum())}")
-    assert differing < 0.03 and abs(mean_ratio - 1.0) < 5e-3
+    assert differing < 0.02 and l2 <= 1e-6 and abs(mean_ratio - 1.0) < 1e-5        # measured: <= 0.33 % of the pixels, last bits only (rel-L2 1e-8)
     # same thing traced as one 4-pass wave (the medium id travels with the ray through the wave slots)
     q = pt.Pathtracer(blob, config=cfg); q.reserve_wave(4); q.render_frame(3); q.sync()
     assert bits_equal(q.get_aov(0)[:, :w], p.get_aov(0)[:, :w])
