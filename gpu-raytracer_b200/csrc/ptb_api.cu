@@ -32,9 +32,23 @@ struct DriverApi {
     CUresult (*Memcpy2D)(const CUDA_MEMCPY2D*) = nullptr;
     CUresult (*TexObjectCreate)(CUtexObject*, const CUDA_RESOURCE_DESC*, const CUDA_TEXTURE_DESC*, const CUDA_RESOURCE_VIEW_DESC*) = nullptr;
     CUresult (*TexObjectDestroy)(CUtexObject) = nullptr;
+    CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
     bool ok = false;
 };
 static DriverApi g_drv;
+// 2-D tensor map over one pitch x height float4 plane, seen as float32 [height][pitch * 4]; box = box_w texels x box_h rows;
+// out-of-range texels are filled with zeros by the copy engine
+static int encode_tile_map_impl(CUtensorMap* map, const void* plane, int pitch, int height, int box_w, int box_h) {
+    if (!g_drv.TensorMapEncodeTiled || (reinterpret_cast<size_t>(plane) & 15) || box_w * 4 > 256 || box_h > 256) return 1;
+    cuuint64_t dims[2] = { (cuuint64_t)pitch * 4, (cuuint64_t)height };
+    cuuint64_t strides[1] = { (cuuint64_t)pitch * 16 };
+    cuuint32_t box[2] = { (cuuint32_t)box_w * 4, (cuuint32_t)box_h };
+    cuuint32_t elem[2] = { 1, 1 };
+    CUresult r = g_drv.TensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(plane), dims, strides, box, elem,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 1;
+}
 static int load_driver_api() {
     if (g_drv.ok) return 0;
     struct { const char* name; void** slot; } want[] = {
@@ -47,6 +61,15 @@ static int load_driver_api() {
         if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !*w.slot) { fprintf(stderr, "[ptb] driver entry point %s unavailable\n", w.name); return PTB_E_STATE; }
     }
     g_drv.ok = true;
+    {   // optional: tensor-map TMA for the SVGF tiles (the filter falls back to plain staging loads without it)
+        cudaDriverEntryPointQueryResult q; void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && fn &&
+            !(getenv("PTB_SVGF_TMA") && atoi(getenv("PTB_SVGF_TMA")) == 0)) {
+            g_drv.TensorMapEncodeTiled = reinterpret_cast<decltype(g_drv.TensorMapEncodeTiled)>(fn);
+            encode_tile_map = encode_tile_map_impl;
+        }
+        cudaGetLastError();
+    }
     return 0;
 }
 
@@ -77,6 +100,7 @@ struct ptb_ctx {
     cudaArray_t lut_arrays[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     bool luts_ready = false;
     uint4* tap_hits = nullptr;
+    uchar4* present_buf = nullptr;                    // tone-mapped 8-bit frame (ptb_present), allocated on first use
     long long launches = 0;
     bool stats_mode = false;
     struct FrameGraph { int first, passes; cudaGraphExec_t exec; long long launches; };
@@ -271,8 +295,8 @@ static void preload_kernels() {
     preload(k_bin_count<false>); preload(k_bin_count<true>); preload(k_bin_scatter<false>); preload(k_bin_scatter<true>);
     preload(k_tap_primary_hits); preload(k_export_rows); preload(k_assemble_rows);
     preload(k_exchange_wait); preload(k_svgf_push); preload(k_svgf_wait_arrivals); preload(k_svgf_push_display);
-    preload(k_svgf_reproject); preload(k_svgf_variance); preload(k_svgf_atrous<0>); preload(k_svgf_atrous<1>); preload(k_svgf_atrous<2>); preload(k_svgf_finalize); preload(k_taa); preload(k_taa_finalize);
-    preload(k_clear_framebuffers); preload(k_apply_uploads);
+    preload(k_svgf_reproject); preload(k_svgf_variance); preload(k_svgf_atrous<0, false>); preload(k_svgf_atrous<1, false>); preload(k_svgf_atrous<2, false>); preload(k_svgf_atrous<1, true>); preload(k_svgf_atrous<2, true>); preload(k_svgf_finalize); preload(k_taa); preload(k_taa_finalize);
+    preload(k_clear_framebuffers); preload(k_apply_uploads); preload(k_present);
     preload(k_integrate_dielectric); preload(k_average_dielectric); preload(k_integrate_conductor); preload(k_average_conductor); preload(k_dump_luts);
     cudaGetLastError();
 }
@@ -799,7 +823,7 @@ extern "C" int ptb_resize(ptb_ctx* ctx, int width, int height) {
     ctx->film_allocs.clear();
     Frame& F = ctx->F;
     for (int k = 0; k < PTB_AOV_COUNT; k++) { F.aov[k].fb = nullptr; F.aov[k].acc = nullptr; }
-    F.display = nullptr; ctx->tap_hits = nullptr;
+    F.display = nullptr; ctx->tap_hits = nullptr; ctx->present_buf = nullptr;
     { float vp[16], vpp[16]; memcpy(vp, F.svgf.view_projection, 64); memcpy(vpp, F.svgf.view_projection_prev, 64);
       memset(&F.svgf, 0, sizeof(F.svgf)); memcpy(F.svgf.view_projection, vp, 64); memcpy(F.svgf.view_projection_prev, vpp, 64); }
     F.width = width; F.height = height;
@@ -1258,6 +1282,25 @@ extern "C" int ptb_download(ptb_ctx* ctx, int aov_type, int accumulated, float* 
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+// What the window does with a frame before showing or capturing it as LDR (Src/Shaders/post.frag, Src/Main.cpp:195-225): tone-map the
+// displayed image (or, with several ranks, the gathered frame) to 8-bit RGBA on the device; optional copy to host (pitch x height x 4 B).
+extern "C" int ptb_present(ptb_ctx* ctx, void** device_rgba8, void* host_dst) {
+    if (!ctx) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t pixels = (size_t)ctx->F.pitch * ctx->F.height;
+    if (!ctx->present_buf) { int e = film_alloc(ctx, &ctx->present_buf, pixels); if (e) return e; }
+    const float4* src = ctx->F.display;
+    if (ctx->F.xchg.count > 0 && ctx->xchg_frames > 0) { void* p = nullptr; int e = ptb_exchange_frame(ctx, &p, nullptr); if (e) return e; src = static_cast<const float4*>(p); }
+    k_present<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(ctx->F, src, ctx->present_buf); ctx->launches++;
+    CK(cudaGetLastError());
+    if (device_rgba8) *device_rgba8 = ctx->present_buf;
+    if (host_dst) {
+        CK(cudaMemcpyAsync(host_dst, ctx->present_buf, pixels * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
 // set_pixel_query (Integrator.h:266-277) / the read-back in Integrator::update (Integrator.cpp:483-494)
 extern "C" int ptb_set_pixel_query(ptb_ctx* ctx, int x, int y) {
     if (!ctx || x < 0 || y < 0 || x >= ctx->F.width || y >= ctx->F.height) return PTB_E_BADARG;

@@ -3,6 +3,7 @@
 // HBM arrays (the reference uses CUDA surfaces bound to arrays); reads past the edge clamp like cudaBoundaryModeClamp.
 // All kernels are 1-D grid-stride over the pitch x height pixel grid, rows contiguous -> coalesced 128-bit accesses.
 #pragma once
+#include <cuda.h>
 #include "ptb_kernels.cuh"
 
 #define PTB_SVGF_EPS 1e-8f
@@ -197,16 +198,51 @@ __global__ void __launch_bounds__(256) k_svgf_variance(const __grid_constant__ F
 // plane); for the dense strides 1 and 2 the tile and its halo of the three input planes are staged in shared memory first
 // (38 x 14 resp. 36 x 12 texels of 16 B per plane: every texel is fetched from L2 once per CTA instead of up to 9 times per warp).
 // The arithmetic and its order are SVGF.h:416-554's -- the outputs are compared bit for bit with the reference kernels.
-template <int STEP_TILED>
-__global__ void __launch_bounds__(256) k_svgf_atrous(const __grid_constant__ Frame P, const float4* din, const float4* iin, float4* dout, float4* iout, int step) {
+// The three tensor maps (2-D, float32 view of a pitch x height float4 plane, box = tile + halo) are only read by the TMA variant.
+struct AtrousMaps { CUtensorMap direct, indirect, normal_depth; };
+PTB_DI void tma_load_tile(void* dst, const CUtensorMap* map, int x_float, int y, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(x_float), "r"(y) : "memory");
+}
+template <int STEP_TILED, bool TMA>
+__global__ void __launch_bounds__(256) k_svgf_atrous(const __grid_constant__ Frame P, const float4* din, const float4* iin, float4* dout, float4* iout, int step,
+                                                     const __grid_constant__ AtrousMaps maps) {
     constexpr int TW = 32, TH = 8;
     constexpr int HALO = STEP_TILED > 0 ? STEP_TILED : 1;             // STEP_TILED = 1 or 2: halo of the taps; the variance blur needs 1
     constexpr int SW = TW + 2 * HALO, SH = TH + 2 * HALO;
-    __shared__ float4 s_d[STEP_TILED > 0 ? SW * SH : 1], s_i[STEP_TILED > 0 ? SW * SH : 1], s_nd[STEP_TILED > 0 ? (SW + 1) * (SH + 1) : 1];
+    __shared__ __align__(128) float4 s_d[STEP_TILED > 0 ? SW * SH : 1];
+    __shared__ __align__(128) float4 s_i[STEP_TILED > 0 ? SW * SH : 1];
+    __shared__ __align__(128) float4 s_nd[STEP_TILED > 0 ? (SW + 1) * (SH + 1) : 1];
+    __shared__ __align__(8) unsigned long long s_bar;
+    if (TMA && STEP_TILED > 0) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    unsigned phase = 0;
     const int tiles_x = (P.width + TW - 1) / TW, tiles_y = (svgf_rows(P) + TH - 1) / TH;
     for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
         const int tx0 = (tile % tiles_x) * TW, ty0 = P.svgf.ext_y0 + (tile / tiles_x) * TH;
-        if (STEP_TILED > 0) {
+        if (STEP_TILED > 0 && TMA) {
+            // 2-D TMA: one elected thread posts the three tile + halo boxes (texels outside the plane arrive as zeros and are never
+            // read: every tap below uses a clamped or range-checked coordinate); everybody waits on the mbarrier's phase
+            __syncthreads();                                          // previous tile's readers are done
+            if (threadIdx.x == 0) {
+                constexpr unsigned bytes = unsigned(sizeof(float4)) * (2u * SW * SH + (SW + 1) * (SH + 1));
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(bytes) : "memory");
+                tma_load_tile(s_d, &maps.direct, (tx0 - HALO) * 4, ty0 - HALO, &s_bar);
+                tma_load_tile(s_i, &maps.indirect, (tx0 - HALO) * 4, ty0 - HALO, &s_bar);
+                tma_load_tile(s_nd, &maps.normal_depth, (tx0 - HALO) * 4, ty0 - HALO, &s_bar);
+            }
+            unsigned done = 0;
+            while (!done) {
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done) : "r"(smem_u32(&s_bar)), "r"(phase) : "memory");
+            }
+            phase ^= 1u;
+        } else if (STEP_TILED > 0) {
             __syncthreads();                                          // previous tile's readers are done
             for (int t = threadIdx.x; t < SW * SH; t += 256) {
                 int sx = t % SW, sy = t / SW;
@@ -390,6 +426,29 @@ __global__ void __launch_bounds__(256) k_clear_framebuffers(const __grid_constan
 }
 
 // launch sequence of the SVGF branch of Pathtracer::render (Pathtracer.cpp:798-837)
+// The window's post-processing pass (Src/Shaders/post.frag:18-41): clamp to >= 0, ACES filmic curve, gamma 2.2; written as 8-bit RGBA
+// like the GL frame buffer the reference presents.  Row 0 = bottom of the image, as everywhere on the device.
+__global__ void __launch_bounds__(256) k_present(const __grid_constant__ Frame P, const float4* src, uchar4* out) {
+    const int total = P.pitch * P.height;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float4 c = src[i];
+        float v[3] = { fmaxf(c.x, 0.0f), fmaxf(c.y, 0.0f), fmaxf(c.z, 0.0f) };
+        unsigned char o[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float x = v[k];
+            float t = __saturatef((x * (2.51f * x + 0.03f)) / (x * (2.43f * x + 0.59f) + 0.14f));
+            o[k] = (unsigned char)__float2uint_rn(255.0f * powf(t, 1.0f / 2.2f));
+        }
+        out[i] = make_uchar4(o[0], o[1], o[2], 255);
+    }
+}
+
+// host hook: builds the 2-D tensor map of one float4 plane for a box of box_w x box_h texels (set by ptb_api.cu when the driver offers
+// cuTensorMapEncodeTiled; nullptr = stage the tiles with plain loads)
+typedef int (*EncodeTileMapFn)(CUtensorMap* map, const void* plane, int pitch, int height, int box_w, int box_h);
+static EncodeTileMapFn encode_tile_map = nullptr;
+
 static int launch_svgf(Frame& F, cudaStream_t st, int sample_index, int grid, long long* launches) {
     // world > 1: tile-local filter.  Every rank stores the rows it traced into the input planes of the ranks that filter them
     // (block + halo), filters ITS block of rows, reads last frame's history across block borders from the owning rank, and ships
@@ -407,9 +466,14 @@ static int launch_svgf(Frame& F, cudaStream_t st, int sample_index, int grid, lo
         float4* t = din; din = dout; dout = t; t = iin; iin = iout; iout = t;
     }
     for (int i = 0; i < F.config.num_atrous_iterations; i++) {
-        if (i == 0)      k_svgf_atrous<1><<<grid, 256, 0, st>>>(F, din, iin, dout, iout, 1);
-        else if (i == 1) k_svgf_atrous<2><<<grid, 256, 0, st>>>(F, din, iin, dout, iout, 2);
-        else             k_svgf_atrous<0><<<grid, 256, 0, st>>>(F, din, iin, dout, iout, 1 << i);
+        AtrousMaps maps; memset(&maps, 0, sizeof(maps));
+        const int halo = i + 1;                    // strides 1 and 2 are staged in shared memory
+        bool tma = i < 2 && encode_tile_map && encode_tile_map(&maps.direct, din, F.pitch, F.height, 32 + 2 * halo, 8 + 2 * halo) == 0 &&
+                   encode_tile_map(&maps.indirect, iin, F.pitch, F.height, 32 + 2 * halo, 8 + 2 * halo) == 0 &&
+                   encode_tile_map(&maps.normal_depth, F.svgf.in_normal_depth, F.pitch, F.height, 32 + 2 * halo + 1, 8 + 2 * halo + 1) == 0;
+        if (i == 0)      { if (tma) k_svgf_atrous<1, true><<<grid, 256, 0, st>>>(F, din, iin, dout, iout, 1, maps); else k_svgf_atrous<1, false><<<grid, 256, 0, st>>>(F, din, iin, dout, iout, 1, maps); }
+        else if (i == 1) { if (tma) k_svgf_atrous<2, true><<<grid, 256, 0, st>>>(F, din, iin, dout, iout, 2, maps); else k_svgf_atrous<2, false><<<grid, 256, 0, st>>>(F, din, iin, dout, iout, 2, maps); }
+        else             k_svgf_atrous<0, false><<<grid, 256, 0, st>>>(F, din, iin, dout, iout, 1 << i, maps);
         (*launches)++;
         float4* t = din; din = dout; dout = t; t = iin; iin = iout; iout = t;
     }

@@ -69,7 +69,7 @@ class PtbTraversalStats(ctypes.Structure):
 
 # every symbol include/ptb.h declares (tests check the built library exports exactly these)
 ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_reserve_wave", "ptb_set_ray_ordering", "ptb_set_static_merge", "ptb_set_intersector", "ptb_resize", "ptb_render_frame",
-               "ptb_measure_traversal", "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_download", "ptb_get_ray_stats", "ptb_set_pixel_query", "ptb_get_pixel_query", "ptb_get_stream", "ptb_export_rows",
+               "ptb_measure_traversal", "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_present", "ptb_download", "ptb_get_ray_stats", "ptb_set_pixel_query", "ptb_get_pixel_query", "ptb_get_stream", "ptb_export_rows",
                "ptb_assemble_rows", "ptb_exchange_create", "ptb_exchange_connect", "ptb_exchange_connect_ipc", "ptb_exchange_frame", "ptb_exchange_disconnect", "ptb_debug_read", "ptb_launch_count", "ptb_set_timing", "ptb_get_stage_ms", "ptb_stage_name",
                "ptb_error_string"]
 
@@ -101,6 +101,7 @@ def lib():
         l.ptb_get_aov.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(ci)]
         l.ptb_get_display.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci)]
         l.ptb_download.argtypes = [vp, ci, ci, vp]
+        l.ptb_present.argtypes = [vp, ctypes.POINTER(vp), vp]
         l.ptb_get_ray_stats.argtypes = [vp, ctypes.POINTER(PtbRayStats), ci]
         l.ptb_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
         l.ptb_set_pixel_query.argtypes = [vp, ci, ci]
@@ -286,6 +287,13 @@ class Pathtracer:
     def get_display(self):
         out = np.empty((self.screen_height, self.screen_pitch, 4), dtype=np.float32)
         _check(lib().ptb_download(self._ctx, -1, 1, out.ctypes.data), "ptb_download")
+        return out
+
+    def present(self):
+        """The frame as the reference's window shows it (post.frag: ACES tone mapping + gamma), 8-bit RGBA [height, pitch, 4],
+        tone-mapped on the device (ptb_present)."""
+        out = np.empty((self.screen_height, self.screen_pitch, 4), dtype=np.uint8)
+        _check(lib().ptb_present(self._ctx, None, out.ctypes.data), "ptb_present")
         return out
 
     def aov_device_ptr(self, aov_type, accumulated=True):

@@ -158,6 +158,10 @@ int  ptb_get_aov(ptb_ctx* ctx, int aov_type, int accumulated, void** device_ptr,
 int  ptb_get_display(ptb_ctx* ctx, void** device_ptr, int* pitch);
 /* Copies an AOV (or the display image when aov_type < 0) to host memory: pitch x height x float4 */
 int  ptb_download(ptb_ctx* ctx, int aov_type, int accumulated, float* host_dst);
+/* The window's post-processing pass (Src/Shaders/post.frag:18-41: clamp >= 0, ACES filmic curve, gamma 2.2) applied on the device to the
+ * displayed frame (with several ranks: the gathered frame), 8-bit RGBA, pitch x height, row 0 = bottom.  device_rgba8 (may be NULL)
+ * receives the device pointer; host_dst (may be NULL) a blocking copy.  What the reference captures as .ppm (Src/Main.cpp:195-225). */
+int  ptb_present(ptb_ctx* ctx, void** device_rgba8, void* host_dst);
 /* set_pixel_query(x, y) (Integrator.h:266-277): the next rendered pass records which (mesh_id, triangle_id) the primary ray of that
  * pixel hits (kernel_sort, Pathtracer.cu:345-348).  ptb_get_pixel_query blocks, returns them (-1, -1 = sky or nothing rendered yet)
  * and clears the query like Integrator::update does (Integrator.cpp:483-494); mesh_id is the instance index in TLAS leaf order. */

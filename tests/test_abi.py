@@ -71,6 +71,14 @@ def test_no_texture_waterfall_clobber_in_sass():
     assert sass_scan.scan(build.build_cuda()) == []
 
 
+def test_library_contains_tensor_map_tma():
+    """The SVGF tile staging uses 2-D tensor-map TMA (cp.async.bulk.tensor.2d -> SASS UTMALDG), the TLAS staging the 1-D bulk copy (UBLKCP)."""
+    import subprocess
+    from gpu_raytracer_b200 import build
+    sass = subprocess.run(["cuobjdump", "-sass", build.build_cuda()], capture_output=True, text=True).stdout
+    assert sass.count("UTMALDG") >= 6 and "UBLKCP" in sass
+
+
 def test_cpp_facade_builds_and_exports_the_reference_entry_points():
     """host/ptb_pathtracer.{h,cpp}: the compiled C++ facade carries the reference's Integrator / Pathtracer entry points."""
     import subprocess

@@ -117,6 +117,29 @@ def test_multi_pass_waves_are_bit_identical_to_pass_by_pass(wave, world):
     base.close()
 
 
+def test_present_and_capture(tmp_path):
+    """ptb_present: the device-side tone mapping (post.frag: ACES + gamma, 8-bit RGBA) agrees with the numpy restatement to one
+    code value; exporters.capture writes what the reference's capture writes (Main.cpp:195-249): tone-mapped .ppm, linear .exr and
+    the AOV .exr files, which read back as the HALF-rounded frame."""
+    from gpu_raytracer_b200 import exporters as ex
+    d = scene.procedural_scene("cornell", seed=2, width=160, height=120)
+    blob = scene.build_blob(d, 8, rng="fallback")
+    p = pt.Pathtracer(blob, config=pt.default_config(num_bounces=3, aov_mask=0x3F)); p.render_frames(4)
+    w, h = 160, 120
+    ldr = p.present()[:h, :w]
+    frame = p.get_display()[:h, :w, :3]
+    want = np.rint(255.0 * ex.tonemap_aces(frame).astype(np.float64)).astype(np.int32)
+    assert (ldr[..., 3] == 255).all() and np.abs(ldr[..., :3].astype(np.int32) - want).max() <= 1
+    assert ldr[..., :3].max() > 40                                  # something was rendered
+    files = ex.capture(p, str(tmp_path / "shot.exr"))
+    assert [os.path.basename(f) for f in files] == ["shot.exr", "albedo.exr", "normal.exr", "position.exr"]
+    assert np.array_equal(ex.load_exr(files[0]), frame.astype(np.float16).astype(np.float32))
+    assert np.array_equal(ex.load_exr(files[2]), p.get_aov(pt.AOV_NORMAL)[:h, :w, :3].astype(np.float16).astype(np.float32))
+    ex.capture(p, str(tmp_path / "shot.ppm"))
+    assert np.abs(ex.load_ppm(str(tmp_path / "shot.ppm")).astype(np.int32) - ldr[..., :3].astype(np.int32)).max() <= 1
+    p.close()
+
+
 def test_edge_cases():
     # width not a multiple of 32 (pitch padding), one bounce, no lights, a single triangle
     d = scene.procedural_scene("soup", seed=2, width=70, height=33, detail=0.1)
