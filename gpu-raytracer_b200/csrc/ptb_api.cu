@@ -137,6 +137,8 @@ struct ptb_ctx {
     float4* merge_woop = nullptr;                     // Woop maps of the merged references (ptb_set_intersector)
     int2*   merge_who = nullptr;
     int     intersector = PTB_INTERSECT_MT;
+    int     integrator = PTB_INTEGRATOR_PATHTRACER;   // or PTB_INTEGRATOR_AO (ptb_set_integrator)
+    float   ao_radius = 1.0f;                         // AO.h:94
     int*    merge_slot_instance_dev = nullptr;
     const float4* uploaded_nodes = nullptr;           // device copy of the host's array (kept: the fallback when nothing is merged)
     // pinned staging for the per-frame uploads (ptb_update_instances): the host arrays are copied here during the call and the
@@ -296,7 +298,7 @@ static void preload_kernels() {
     preload(k_tap_primary_hits); preload(k_export_rows); preload(k_assemble_rows);
     preload(k_exchange_wait); preload(k_svgf_push); preload(k_svgf_wait_arrivals); preload(k_svgf_push_display);
     preload(k_svgf_reproject); preload(k_svgf_variance); preload(k_svgf_atrous<0, false>); preload(k_svgf_atrous<1, false>); preload(k_svgf_atrous<2, false>); preload(k_svgf_atrous<1, true>); preload(k_svgf_atrous<2, true>); preload(k_svgf_finalize); preload(k_taa); preload(k_taa_finalize);
-    preload(k_clear_framebuffers); preload(k_apply_uploads); preload(k_present);
+    preload(k_clear_framebuffers); preload(k_apply_uploads); preload(k_present); preload(k_ambient_occlusion);
     preload(k_integrate_dielectric); preload(k_average_dielectric); preload(k_integrate_conductor); preload(k_average_conductor); preload(k_dump_luts);
     cudaGetLastError();
 }
@@ -833,6 +835,16 @@ extern "C" int ptb_resize(ptb_ctx* ctx, int width, int height) {
     return 0;
 }
 
+// The reference's second integrator (Src/Renderer/Integrators/AO.{h,cpp}, Src/CUDA/AO.cu): one cosine-distributed occlusion ray of
+// length `ao_radius` per primary hit.  Same queues, traversal kernels, waves and accumulator as the path tracer.
+extern "C" int ptb_set_integrator(ptb_ctx* ctx, int kind, float ao_radius) {
+    if (!ctx || (kind != PTB_INTEGRATOR_PATHTRACER && kind != PTB_INTEGRATOR_AO) || !(ao_radius > 0.0f)) return PTB_E_BADARG;
+    if (kind == PTB_INTEGRATOR_AO && ctx->F.config.enable_svgf) return PTB_E_STATE;
+    if (kind != ctx->integrator || ao_radius != ctx->ao_radius) drop_graphs(ctx);
+    ctx->integrator = kind; ctx->ao_radius = ao_radius;
+    return 0;
+}
+
 extern "C" int ptb_set_intersector(ptb_ctx* ctx, int kind) {
     if (!ctx || (kind != PTB_INTERSECT_MT && kind != PTB_INTERSECT_WOOP)) return PTB_E_BADARG;
     if (kind == ctx->intersector) return 0;
@@ -1017,9 +1029,10 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
     // again at the next sort (both deposit into the framebuffer: shadow first, to keep the reference's summation order), so the
     // shadow trace runs on a side stream; its CTAs and the next closest-hit trace's CTAs fill each other's ramp-down tails.
     // Per-stage timing (events on the main stream) and the ordering experiment keep everything on one stream.
-    const bool overlap = ctx->overlap_enabled && nee && !ctx->timing && !ctx->stats_mode && F.order_bins == 0;
+    const bool overlap = ctx->overlap_enabled && nee && !ctx->timing && !ctx->stats_mode && F.order_bins == 0 && ctx->integrator != PTB_INTEGRATOR_AO;
     bool side_pending = false;
-    for (int bounce = 0; bounce < F.config.num_bounces; bounce++) {
+    const bool ao = ctx->integrator == PTB_INTEGRATOR_AO;
+    for (int bounce = 0; bounce < (ao ? 1 : F.config.num_bounces); bounce++) {
         const bool ordered = F.order_bins > 0 && ctx->bvh_kind == 8 && bounce < PTB_ORDER_MAX_BOUNCE;
         const unsigned* order_c = ordered && bounce > 0 ? F.order : nullptr;       // primary rays are coherent as generated
         const unsigned* order_s = ordered ? F.order : nullptr;
@@ -1031,15 +1044,16 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
           else                    k_trace2<false, false><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
           ctx->launches++; }
         if (side_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); side_pending = false; }     // shadow[bounce-1] deposits before sort[bounce]
-        { StageTimer t(ctx, ST_SORT); k_sort<<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
-        { StageTimer t(ctx, ST_SHADE);
+        if (ao) { StageTimer t(ctx, ST_SHADE); k_ambient_occlusion<<<g1d, 256, 0, st>>>(F, ctx->ao_radius); ctx->launches++; }
+        else { StageTimer t(ctx, ST_SORT); k_sort<<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
+        if (!ao) { StageTimer t(ctx, ST_SHADE);
           if (ctx->has_type[0]) { k_shade<BSDFDiffuse><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
           if (ctx->has_type[1]) { k_shade<BSDFPlastic><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
           if (ctx->has_type[2]) { k_shade<BSDFDielectric><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; }
           if (ctx->has_type[3]) { k_shade<BSDFConductor><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches++; } }
         if (nee && order_s) { StageTimer t(ctx, ST_ORDER);
           k_bin_count<true><<<g1d, 256, 0, st>>>(F, bounce); k_bin_scatter<true><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches += 2; }
-        if (nee) {
+        if (nee || ao) {
             StageTimer t(ctx, ST_SHADOW);
             cudaStream_t ss = st;
             if (overlap) { CK(cudaEventRecord(ctx->ev_fork, st)); CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0)); ss = ctx->side_stream; }

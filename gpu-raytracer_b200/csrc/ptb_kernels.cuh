@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                             if (STATS) st_miss++;
                             float4 ill = P.sq.illum[ray_index];
                             int px = word_fb_index(P, __float_as_uint(P.sq.od1[ray_index].w));
-                            float4 v = make_float4(ill.x, ill.y, ill.z, 0.0f);
+                            float4 v = make_float4(ill.x, ill.y, ill.z, ill.w);
                             aov_add(P, PTB_AOV_RADIANCE, px, v);
                             if (bounce == 0) aov_set(P, PTB_AOV_RADIANCE_DIRECT, px, v);
                             else             aov_add(P, PTB_AOV_RADIANCE_INDIRECT, px, v);
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                 if (STATS) st_miss++;
                 float4 ill = P.sq.illum[ray_index];
                 int px = word_fb_index(P, __float_as_uint(b.w));
-                float4 v = make_float4(ill.x, ill.y, ill.z, 0.0f);
+                float4 v = make_float4(ill.x, ill.y, ill.z, ill.w);
                 aov_add(P, PTB_AOV_RADIANCE, px, v);
                 if (bounce == 0) aov_set(P, PTB_AOV_RADIANCE_DIRECT, px, v);
                 else             aov_add(P, PTB_AOV_RADIANCE_INDIRECT, px, v);
@@ -1123,6 +1123,57 @@ __global__ void __launch_bounds__(256, ShadeOccupancy<BSDF>::min_blocks) k_shade
             qn.od0[n_slot] = nx0; qn.od1[n_slot] = nx1; qn.path[n_slot] = nx_path; qn.pix[n_slot] = nx_pix;
             if (nx_medium != PTB_INVALID) qn.medium[n_slot] = nx_medium;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ ambient occlusion integrator
+// The reference's second integrator (Src/CUDA/AO.cu:116-184, host Src/Renderer/Integrators/AO.cpp:143-192): primary hit -> one
+// cosine-distributed occlusion ray of length ao_radius; an unoccluded ray sets the pixel to 1.  Reuses the wavefront machinery:
+// k_generate -> k_trace8 / k_trace2 -> k_ambient_occlusion -> shadow trace (deposit) -> k_accumulate, waves included.
+__global__ void __launch_bounds__(256) k_ambient_occlusion(const __grid_constant__ Frame P, float ao_radius) {
+    const RayQueue& q = P.q[0];
+    const int count = P.counters->trace[0];
+    const int rounded = (count + 31) & ~31;
+    for (int index = blockIdx.x * blockDim.x + threadIdx.x; index < rounded; index += gridDim.x * blockDim.x) {
+        bool emit = false;
+        float4 sh0, sh1;
+        if (index < count) {
+            float4 a = q.od0[index], b = q.od1[index];
+            float3 ray_direction = f3(a.w, b.x, b.y);
+            Hit hit = unpack_hit(__ldg(q.hit + index));
+            unsigned pf = q.pix[index];
+            const int pixel_index = word_pixel(P, pf);
+            const int fbi = word_fb_index(P, pf);
+            const int sample_index = P.first_sample + word_slot(P, pf);
+            if (hit.triangle_id != PTB_INVALID) {
+                if (P.pixel_query[0] == pixel_index && word_slot(P, pf) == 0) { P.pixel_query[1] = hit.mesh_id; P.pixel_query[2] = hit.triangle_id; }
+                TriFull tri = load_tri_full(P, hit.triangle_id);
+                float3 gn = normalize(cross(tri.e1, tri.e2));                 // mesh space, like the reference (AO.cu:136)
+                float3 hit_point = barycentric(hit.u, hit.v, tri.p0, tri.e1, tri.e2);
+                float3 hit_normal = barycentric(hit.u, hit.v, tri.n0, tri.ne1, tri.ne2);
+                Mat3x4 world = load_mat(P.mesh_transforms, hit.mesh_id);
+                hit_point = xform_pos(world, hit_point);
+                hit_normal = xform_dir(world, hit_normal);
+                hit_normal = normalize(hit_normal);
+                if (dot(ray_direction, hit_normal) > 0.0f) hit_normal = -hit_normal;
+                aov_set(P, PTB_AOV_NORMAL, fbi, f4(hit_normal));
+                aov_set(P, PTB_AOV_POSITION, fbi, f4(hit_point));
+                float3 tangent, bitangent;
+                orthonormal_basis(hit_normal, tangent, bitangent);
+                float2 r = rng2<DIM_BSDF_0>(P, pixel_index, 0, sample_index);
+                float3 wo = sample_cosine_hemisphere(r.x, r.y);
+                float3 dir_out = local_to_world(wo, tangent, bitangent, hit_normal);
+                float pdf = wo.z * PTB_ONE_OVER_PI;
+                if (pdf_is_valid(pdf)) {
+                    float3 org = ray_origin_epsilon_offset(hit_point, dir_out, gn);
+                    emit = true;
+                    sh0 = make_float4(org.x, org.y, org.z, dir_out.x);
+                    sh1 = make_float4(dir_out.y, dir_out.z, ao_radius, __uint_as_float(pf & ~PTB_FLAGS_ALL));
+                }
+            }
+        }
+        int slot = warp_append(&P.counters->shadow[0], emit);
+        if (emit) { P.sq.od0[slot] = sh0; P.sq.od1[slot] = sh1; P.sq.illum[slot] = make_float4(1.0f, 1.0f, 1.0f, 1.0f); }
     }
 }
 

@@ -68,7 +68,7 @@ class PtbTraversalStats(ctypes.Structure):
 
 
 # every symbol include/ptb.h declares (tests check the built library exports exactly these)
-ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_reserve_wave", "ptb_set_ray_ordering", "ptb_set_static_merge", "ptb_set_intersector", "ptb_resize", "ptb_render_frame",
+ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_reserve_wave", "ptb_set_ray_ordering", "ptb_set_static_merge", "ptb_set_integrator", "ptb_set_intersector", "ptb_resize", "ptb_render_frame",
                "ptb_measure_traversal", "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_present", "ptb_download", "ptb_get_ray_stats", "ptb_set_pixel_query", "ptb_get_pixel_query", "ptb_get_stream", "ptb_export_rows",
                "ptb_assemble_rows", "ptb_exchange_create", "ptb_exchange_connect", "ptb_exchange_connect_ipc", "ptb_exchange_frame", "ptb_exchange_disconnect", "ptb_debug_read", "ptb_launch_count", "ptb_set_timing", "ptb_get_stage_ms", "ptb_stage_name",
                "ptb_error_string"]
@@ -95,6 +95,7 @@ def lib():
         l.ptb_set_ray_ordering.argtypes = [vp, ci]
         l.ptb_set_static_merge.argtypes = [vp, ci]
         l.ptb_set_intersector.argtypes = [vp, ci]
+        l.ptb_set_integrator.argtypes = [vp, ci, ctypes.c_float]
         l.ptb_resize.argtypes = [vp, ci, ci]
         l.ptb_measure_traversal.argtypes = [vp, ci, ctypes.POINTER(PtbTraversalStats)]
         l.ptb_sync.argtypes = [vp]
@@ -354,6 +355,11 @@ class Pathtracer:
         self._view_projection_prev = self._view_projection.copy()
         self.invalidated_camera = True; self.invalidated_gpu_config = True
         self.sample_index = 0
+
+    def set_integrator(self, kind, ao_radius=1.0):
+        """include/ptb.h: ptb_set_integrator -- "pathtracer" (default) or "ao" (the reference's ambient-occlusion integrator, AO.cu)."""
+        _check(lib().ptb_set_integrator(self._ctx, {"pathtracer": 0, "ao": 1}[kind] if isinstance(kind, str) else int(kind), float(ao_radius)), "ptb_set_integrator")
+        self.invalidated_gpu_config = True
 
     def set_intersector(self, kind):
         """include/ptb.h: ptb_set_intersector -- "mt" (reference's Moeller-Trumbore, default) or "woop" (merged BVH only)."""

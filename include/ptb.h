@@ -191,6 +191,12 @@ int  ptb_set_static_merge(ptb_ctx* ctx, int mode);
  * Accumulators, SVGF / TAA history and cached frame graphs start over; set the camera for the new film afterwards (Camera::resize)
  * and restart sample_index at 0.  Not allowed while a frame exchange is connected (PTB_E_STATE). */
 int  ptb_resize(ptb_ctx* ctx, int width, int height);
+/* Which integrator ptb_render / ptb_render_frame run.  PTB_INTEGRATOR_PATHTRACER (default): Pathtracer::render.  PTB_INTEGRATOR_AO: the
+ * reference's ambient-occlusion integrator (Src/CUDA/AO.cu:49-184, Src/Renderer/Integrators/AO.cpp:143-192): primary hit, one
+ * cosine-distributed occlusion ray of length ao_radius (AO.h:94: 1.0), RADIANCE = 1 where it escapes; NORMAL / POSITION AOVs as there. */
+#define PTB_INTEGRATOR_PATHTRACER 0
+#define PTB_INTEGRATOR_AO         1
+int  ptb_set_integrator(ptb_ctx* ctx, int kind, float ao_radius);
 #define PTB_INTERSECT_MT   0
 #define PTB_INTERSECT_WOOP 1
 int  ptb_set_intersector(ptb_ctx* ctx, int kind);

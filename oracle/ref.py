@@ -18,6 +18,13 @@ def available():
     return os.path.exists(CUBIN)
 
 
+CUBIN_AO = os.path.join(_HERE, "_ref", "ao_ref.cubin")      # Src/CUDA/AO.cu, unmodified: the reference's ambient-occlusion integrator
+
+
+def ao_available():
+    return os.path.exists(CUBIN_AO)
+
+
 def uniform_available():
     return os.path.exists(CUBIN_UNIFORM)
 
@@ -140,3 +147,27 @@ class Reference:
         if self._ctx.value:
             lib().ref_destroy(self._ctx)
             self._ctx = ctypes.c_void_p()
+
+
+class ReferenceAO(Reference):
+    """The reference's AO integrator (oracle/_ref/ao_ref.cubin) behind the same surface: render_pass / get_aov / ray_stats."""
+
+    def __init__(self, blob, config=None, device=0, ao_radius=1.0):
+        from gpu_raytracer_b200 import pathtracer as pt
+        self._pt = pt
+        l = lib()
+        self.ao_radius = float(ao_radius)
+        self.width, self.height = int(blob["width"]), int(blob["height"])
+        self.pitch = (self.width + 31) // 32 * 32
+        self._ctx = ctypes.c_void_p()
+        self._ck(l.ref_create(ctypes.byref(self._ctx), CUBIN_AO.encode(), device, self.width, self.height), "ref_create")
+        keep = []
+        scene = pt.fill_scene_struct(blob, keep)
+        self._ck(l.ref_ao_upload_scene(self._ctx, ctypes.byref(scene)), "ref_ao_upload_scene")
+        self.config = config or pt.default_config(num_bounces=1)
+        self._ck(l.ref_set_config(self._ctx, ctypes.byref(self.config)), "ref_set_config")
+        cam = pt.camera_struct(blob["camera"])
+        self._ck(l.ref_set_camera(self._ctx, ctypes.byref(cam), None, None), "ref_set_camera")
+
+    def render_pass(self, sample_index):
+        self._ck(lib().ref_ao_render(self._ctx, int(sample_index), ctypes.c_float(self.ao_radius)), "ref_ao_render")

@@ -608,6 +608,93 @@ int ref_read_global_buffer(ref_ctx* c, const char* global_name, void* dst, size_
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------------
+// The reference's ambient-occlusion integrator: Src/CUDA/AO.cu compiled unmodified into oracle/_ref/ao_ref.cubin, driven with the
+// launch sequence of AO::render (Src/Renderer/Integrators/AO.cpp:143-192).  Create the context with ref_create(..., ao cubin, ...),
+// then ref_ao_upload_scene / ref_set_config / ref_set_camera / ref_ao_render; downloads and ray statistics as for the path tracer.
+struct BufferSizesAO { int trace, shadow, rays_retired, rays_retired_shadow; };   // AO.cu:33-40
+struct DevTraceBufferAO { DevSoA3 origin, direction; CUdeviceptr hits, pixel_index; };
+struct DevShadowBufferAO { DevSoA3 origin, direction; CUdeviceptr max_distance, pixel_index; };
+
+int ref_ao_upload_scene(ref_ctx* c, const ptb_scene* s) {
+    RCK(cuCtxSetCurrent(c->cu));
+    int e = 0;
+    c->bvh_kind = s->bvh_kind;
+    e |= set_global(c, "screen_width", c->width); e |= set_global(c, "screen_pitch", c->pitch); e |= set_global(c, "screen_height", c->height);
+    if (e) return e;
+    e |= get_kernel(c, c->generate, "kernel_generate");
+    e |= get_kernel(c, c->trace, s->bvh_kind == 8 ? "kernel_trace_bvh8" : "kernel_trace_bvh2");
+    e |= get_kernel(c, c->trace_shadow, s->bvh_kind == 8 ? "kernel_trace_shadow_bvh8" : "kernel_trace_shadow_bvh2");
+    e |= get_kernel(c, c->sort, "kernel_ambient_occlusion"); e |= get_kernel(c, c->accumulate, "kernel_accumulate");
+    if (e) return e;
+    size_1d_kernel(c->generate); size_1d_kernel(c->sort);
+    e |= size_trace_kernel(c->trace, s->bvh_kind == 8 ? 8 : 4); e |= size_trace_kernel(c->trace_shadow, s->bvh_kind == 8 ? 8 : 4);
+    e |= size_2d_kernel(c, c->accumulate);
+    if (e) return e;
+    CUdeviceptr p;
+    e = dupload(c, &p, s->triangles, (size_t)s->triangle_count * 96); if (e) return e; e = set_global(c, "triangles", p); if (e) return e;
+    e = dupload(c, &p, s->bvh_nodes, (size_t)s->bvh_node_count * (s->bvh_kind == 8 ? 80 : 32)); if (e) return e;
+    e = set_global(c, s->bvh_kind == 8 ? "bvh8_nodes" : "bvh2_nodes", p); if (e) return e;
+    e = dupload(c, &p, s->mesh_bvh_root_indices, (size_t)s->mesh_count * 4); if (e) return e; e = set_global(c, "mesh_bvh_root_indices", p); if (e) return e;
+    e = dupload(c, &p, s->mesh_material_ids, (size_t)s->mesh_count * 4); if (e) return e; e = set_global(c, "mesh_material_ids", p); if (e) return e;
+    e = dupload(c, &p, s->mesh_transforms, (size_t)s->mesh_count * 48); if (e) return e; e = set_global(c, "mesh_transforms", p); if (e) return e;
+    e = dupload(c, &p, s->mesh_transforms_inv, (size_t)s->mesh_count * 48); if (e) return e; e = set_global(c, "mesh_transforms_inv", p); if (e) return e;
+    e = dupload(c, &p, s->mesh_transforms_prev ? s->mesh_transforms_prev : s->mesh_transforms, (size_t)s->mesh_count * 48); if (e) return e;
+    e = set_global(c, "mesh_transforms_prev", p); if (e) return e;
+    e = dupload(c, &p, s->pmj_samples, 64 * 4096 * 8); if (e) return e; e = set_global(c, "pmj_samples", p); if (e) return e;
+    e = dupload(c, &p, s->blue_noise, 16 * 128 * 128 * 2); if (e) return e; e = set_global(c, "blue_noise_textures", p); if (e) return e;
+    DevTraceBufferAO tb; DevShadowBufferAO sb;
+    e |= alloc_soa(c, tb.origin, BATCH_SIZE); e |= alloc_soa(c, tb.direction, BATCH_SIZE); e |= dalloc(c, &tb.hits, (size_t)BATCH_SIZE * 16); e |= dalloc(c, &tb.pixel_index, (size_t)BATCH_SIZE * 4);
+    e |= alloc_soa(c, sb.origin, BATCH_SIZE); e |= alloc_soa(c, sb.direction, BATCH_SIZE); e |= dalloc(c, &sb.max_distance, (size_t)BATCH_SIZE * 4); e |= dalloc(c, &sb.pixel_index, (size_t)BATCH_SIZE * 4);
+    if (e) return 1;
+    c->trace_hits[0] = tb.hits; c->trace_pix[0] = tb.pixel_index;
+    e = set_global(c, "ray_buffer_trace", tb); if (e) return e;
+    e = set_global(c, "ray_buffer_shadow", sb); if (e) return e;
+    e = enable_aov(c, 0); if (e) return e;
+    e = push_aovs(c); if (e) return e;
+    e = make_array(&c->surf_array, c->pitch, c->height, 0, 4, CU_AD_FORMAT_FLOAT, true); if (e) return e;
+    e = make_surface(c->surf_array, &c->surf); if (e) return e;
+    e = set_global(c, "accumulator", c->surf); if (e) return e;
+    BufferSizesAO bs = { c->pixel_count < BATCH_SIZE ? c->pixel_count : BATCH_SIZE, 0, 0, 0 };
+    e = set_global(c, "buffer_sizes", bs); if (e) return e;
+    RCK(cuCtxSynchronize());
+    return 0;
+}
+
+int ref_ao_render(ref_ctx* c, int sample_index, float ao_radius) {
+    RCK(cuCtxSetCurrent(c->cu));
+    CUdeviceptr d_sizes; size_t sz;
+    int e = get_global(c, "buffer_sizes", &d_sizes, &sz); if (e) return e;
+    int pixels_left = c->pixel_count;
+    const int batch_size = c->pixel_count < BATCH_SIZE ? c->pixel_count : BATCH_SIZE;
+    auto harvest = [&]() -> int {
+        BufferSizesAO bs;
+        RCK(cuMemcpyDtoH(&bs, d_sizes, sizeof(bs)));
+        c->total_trace[0] += bs.trace; c->total_shadow[0] += bs.shadow;
+        return 0;
+    };
+    while (pixels_left > 0) {
+        int pixel_offset = c->pixel_count - pixels_left;
+        int pixel_count = batch_size < pixels_left ? batch_size : pixels_left;
+        { void* a[] = { &sample_index, &pixel_offset, &pixel_count }; e = launch(c, c->generate, a); if (e) return e; }
+        e = launch(c, c->trace, nullptr); if (e) return e;
+        { void* a[] = { &sample_index, &ao_radius }; e = launch(c, c->sort, a); if (e) return e; }
+        e = launch(c, c->trace_shadow, nullptr); if (e) return e;
+        pixels_left -= batch_size;
+        e = harvest(); if (e) return e;
+        if (pixels_left > 0) {
+            BufferSizesAO bs = { batch_size < pixels_left ? batch_size : pixels_left, 0, 0, 0 };
+            RCK(cuMemcpyHtoD(d_sizes, &bs, sizeof(bs)));
+        }
+    }
+    { float n = float(sample_index); void* a[] = { &n }; e = launch(c, c->accumulate, a); if (e) return e; }
+    BufferSizesAO bs = { batch_size, 0, 0, 0 };
+    RCK(cuMemcpyHtoD(d_sizes, &bs, sizeof(bs)));
+    for (int k = 0; k < 6; k++) if (c->aov_fb[k]) RCK(cuMemsetD8Async(c->aov_fb[k], 0, (size_t)c->pitch * c->height * 16, nullptr));
+    c->frames++;
+    return 0;
+}
+
 // Pipelined read-back of the displayed frame (what bench.py's e2e leg does for the product arm): the display surface is parked in
 // a linear staging buffer on the render stream (device to device), then copied to pinned host memory on a separate non-blocking
 // stream while the next frame renders.  ref_e2e_wait(slot) blocks until that copy has landed and returns the host pointer.

@@ -484,3 +484,33 @@ def test_woop_intersector_mismatch_rate():
     if ref.available() and os.path.exists(path):
         r = ref.Reference(blob, config=cfg); r.render_frames(8); want = r.get_aov(0)[:, :w, :3]; r.close()
         print(f"[woop] rel-L2 vs reference kernels: woop {rel_l2(wo, want):.3e}, moeller-trumbore {rel_l2(mt, want):.3e}")
+
+
+@pytest.mark.parametrize("scene_kind,bvh", [("atrium", 8), ("cornell", 2)])
+def test_ao_integrator_against_reference_ao_kernels(scene_kind, bvh):
+    """ptb_set_integrator(AO): the reference's second integrator (Src/CUDA/AO.cu compiled unmodified into oracle/_ref/ao_ref.cubin,
+    launch sequence of AO::render): RADIANCE, NORMAL and POSITION accumulators, the display and the ray counters bit-exact over
+    four passes, in both traversal modes, pass by pass and as one wave; CWBVH and binary BVH."""
+    from oracle import ref
+    if not ref.ao_available():
+        pytest.skip("oracle/_ref/ao_ref.cubin not built")
+    d = scene.procedural_scene(scene_kind, seed=6, width=320, height=192, detail=0.5)
+    blob = scene.build_blob(d, bvh, rng="fallback")
+    w = 320
+    cfg = pt.default_config(num_bounces=1, aov_mask=(1 << pt.AOV_RADIANCE) | (1 << pt.AOV_NORMAL) | (1 << pt.AOV_POSITION))
+    r = ref.ReferenceAO(blob, config=cfg, ao_radius=0.75); r.render_frames(4)
+    want = {k: r.get_aov(k)[:, :w] for k in (pt.AOV_RADIANCE, pt.AOV_NORMAL, pt.AOV_POSITION)}
+    wd = r.get_display()[:, :w]; rs = r.ray_stats(); r.close()
+    assert 0.05 < float(want[pt.AOV_RADIANCE][..., 0].mean()) < 0.999          # some rays escape, some are occluded
+    for merge, wave in ((False, 1), (True, 1), (False, 5)):
+        p = pt.Pathtracer(blob, config=cfg); p.set_static_merge(merge); p.set_integrator("ao", 0.75)
+        if wave > 1:
+            p.reserve_wave(wave); p.render_frame(4); p.sync()
+        else:
+            p.render_frames(4)
+        for k, img in want.items():
+            assert bits_equal(p.get_aov(k)[:, :w], img), (merge, wave, pt.AOV_NAMES[k])
+        assert bits_equal(p.get_display()[:, :w], wd)
+        st = p.ray_stats()
+        assert st["trace"][0] == rs["trace"][0] and st["shadow"][0] == rs["shadow"][0]
+        p.close()
