@@ -742,6 +742,36 @@ void* ptbh_build_boxes(const float* aabb, int n, int kind) {
 }
 
 
+// Conversion of an already built binary BVH (the reference's `.bvh` cache, BVHLoader.cpp: raw one-primitive-per-leaf BVH2 + indices) to
+// the kind the kernels walk, without rebuilding: kind 8 -> CWBVH, kind 2 -> SAH leaf collapse (sah_leaf > 0) or a plain copy.
+// nodes: n_nodes x 32 bytes (BVH.h:11-23 layout, node 1 = dummy); returns null on a malformed tree.
+void* ptbh_from_bvh2(const void* nodes, int n_nodes, const int* indices, int n_indices, int kind, float sah_node, float sah_leaf) {
+    if (!nodes || !indices || n_nodes < 1 || n_indices < 1 || (kind != 2 && kind != 8)) return nullptr;
+    BVH2 raw;
+    raw.nodes.resize(size_t(n_nodes)); std::memcpy(raw.nodes.data(), nodes, size_t(n_nodes) * sizeof(Node2));
+    raw.indices.assign(indices, indices + n_indices);
+    {   // every link in range and the graph a tree, so that a damaged file cannot walk out of the arrays or loop (an optimised BVH may
+        // have children stored before their parents: only reachability is checked, not index order)
+        std::vector<int> todo{ 0 };
+        size_t visited = 0;
+        while (!todo.empty()) {
+            int i = todo.back(); todo.pop_back();
+            if (++visited > size_t(n_nodes)) return nullptr;
+            const Node2& nd = raw.nodes[size_t(i)];
+            if (nd.leaf()) { if (nd.left_or_first < 0 || size_t(nd.left_or_first) + nd.count() > size_t(n_indices)) return nullptr; }
+            else {
+                if (nd.left_or_first < 1 || nd.left_or_first + 1 >= n_nodes) return nullptr;
+                todo.push_back(nd.left_or_first); todo.push_back(nd.left_or_first + 1);
+            }
+        }
+    }
+    Built* b = new Built(); b->kind = kind;
+    if (kind == 8) WideConverter(raw, b->bvh8).run();
+    else if (sah_leaf > 0.0f) { Collapser c{ raw, b->bvh2, sah_node, sah_leaf, {} }; c.run(); }
+    else b->bvh2 = std::move(raw);
+    return b;
+}
+
 // Split-BVH build (spatial splits) -> CWBVH.  alpha: minimum overlap of the object split's children, relative to the root's area,
 // for a spatial split to be tried (the reference's --sbvh-alpha, Config.h:58); max_dup: cap on references as a multiple of n
 // (e.g. 1.5).  ptbh_index_count() is the number of REFERENCES (>= n): indices may repeat a triangle.

@@ -60,6 +60,8 @@ def hostlib():
         lib.ptbh_free.argtypes = [ctypes.c_void_p]
         lib.ptbh_build_triangles_sbvh.restype = ctypes.c_void_p
         lib.ptbh_build_triangles_sbvh.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_float]
+        lib.ptbh_from_bvh2.restype = ctypes.c_void_p
+        lib.ptbh_from_bvh2.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float]
         lib.ptbh_trace_stats.restype = None
         lib.ptbh_trace_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _hostlib = lib
@@ -95,6 +97,33 @@ class BuiltBVH:
 def build_blas(positions: np.ndarray, kind: int, sah_node=4.0, sah_leaf=1.0) -> BuiltBVH:
     pos = np.ascontiguousarray(positions, dtype=f32).reshape(-1, 9)
     return BuiltBVH(hostlib().ptbh_build_triangles(pos.ctypes.data, pos.shape[0], kind, sah_node, sah_leaf))
+
+
+def blas_from_bvh2(nodes: np.ndarray, indices: np.ndarray, kind: int, sah_node=4.0, sah_leaf=1.0) -> BuiltBVH:
+    """A raw binary BVH (32-byte nodes + primitive order, e.g. from the reference's `.bvh` cache, bvh_cache.py) converted to the
+    traversal kind without rebuilding (BVH::create_from_bvh2, Src/BVH/BVH.cpp)."""
+    nd = np.ascontiguousarray(nodes).view(np.uint8).reshape(-1)
+    idx = np.ascontiguousarray(indices, dtype=np.int32)
+    return BuiltBVH(hostlib().ptbh_from_bvh2(nd.ctypes.data, nd.size // 32, idx.ctypes.data, idx.size, kind, sah_node, sah_leaf))
+
+
+def build_blas_cached(mesh_file: str, tri, kind: int, sah_node=4.0, sah_leaf=1.0, force_rebuild=False) -> BuiltBVH:
+    """The reference's mesh-load flow (Src/Assets/AssetManager.cpp + BVHLoader.cpp): reuse `<mesh file>.bvh` when it is at least as
+    new as the mesh and was written with the same settings; otherwise build the raw SAH BVH2, write the cache, convert.
+    tri = (positions[F,3,3], normals[F,3,3], tex_coords[F,3,2]) of that mesh file."""
+    from . import bvh_cache
+    p, n, t = tri
+    cached = bvh_cache.try_to_load(mesh_file, bvh_cache.BVH_TYPE_SAH, False, sah_node, sah_leaf, force_rebuild)
+    if cached is not None and cached.triangles.shape[0] == p.shape[0] and np.array_equal(cached.triangles["position"], np.asarray(p, dtype=f32)):
+        return blas_from_bvh2(cached.nodes, cached.indices, kind, sah_node, sah_leaf)
+    raw = build_blas(p, 2, sah_node, 0.0)                     # raw BVH2, one primitive per leaf: what the cache stores
+    nodes, indices = raw.export(0, 0)
+    try:
+        bvh_cache.save(bvh_cache.bvh_filename(mesh_file), bvh_cache.CachedBVH(bvh_cache.pack_triangles(p, n, t), nodes.view(bvh_cache.NODE2_DTYPE), indices,
+                                                                              bvh_cache.BVH_TYPE_SAH, False, sah_node, sah_leaf))
+    except OSError:
+        pass                                                  # read-only asset directory: build every time, like a failed fopen in BVHLoader::save
+    return blas_from_bvh2(nodes, indices, kind, sah_node, sah_leaf)
 
 
 def build_blas_sbvh(positions: np.ndarray, alpha=3e-4, bins=96, max_dup=2.0) -> BuiltBVH:
@@ -560,6 +589,7 @@ class SceneDesc:
 
     def __init__(self):
         self.mesh_datas = []   # list of (p[F,3,3], n[F,3,3], t[F,3,2])
+        self.mesh_files = []   # per mesh data: the file it was loaded from, or None (shapes built in code); keys the `.bvh` cache
         self.materials = [Material(MAT_DIFFUSE, "Default", diffuse=(1, 0, 1))]
         self.media = [dict(sigma_a=(0, 0, 0), sigma_s=(0, 0, 0), g=0.0)]
         self.textures = []
@@ -575,8 +605,8 @@ class SceneDesc:
         self.sky_scale = 1.0
         self.source = "procedural"
 
-    def add_mesh_data(self, tri):
-        self.mesh_datas.append(tri); return len(self.mesh_datas) - 1
+    def add_mesh_data(self, tri, source=None):
+        self.mesh_datas.append(tri); self.mesh_files.append(source); return len(self.mesh_datas) - 1
 
     def add_material(self, m):
         self.materials.append(m); return len(self.materials) - 1
@@ -651,8 +681,9 @@ def pack_triangles(p, n, t):
     return out
 
 
-def build_blob(desc: SceneDesc, bvh_kind=8, width=None, height=None, threads=None, timing=None, rng="auto"):
-    """Flatten a SceneDesc into the device ABI. `timing` (dict) receives the CPU BVH-build seconds."""
+def build_blob(desc: SceneDesc, bvh_kind=8, width=None, height=None, threads=None, timing=None, rng="auto", use_bvh_cache=False):
+    """Flatten a SceneDesc into the device ABI. `timing` (dict) receives the CPU BVH-build seconds.
+    use_bvh_cache: keep / reuse the reference's `<mesh file>.bvh` files next to the meshes (build_blas_cached)."""
     import time
     width = int(width or desc.width); height = int(height or desc.height)
     M = len(desc.instances)
@@ -660,7 +691,9 @@ def build_blob(desc: SceneDesc, bvh_kind=8, width=None, height=None, threads=Non
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as pool:  # one job per mesh data, like the reference's asset pool
-        blas = list(pool.map(lambda tri: build_blas(tri[0], bvh_kind), desc.mesh_datas))
+        files = list(desc.mesh_files) + [None] * (len(desc.mesh_datas) - len(desc.mesh_files))
+        blas = list(pool.map(lambda a: build_blas_cached(a[1], a[0], bvh_kind) if (use_bvh_cache and a[1]) else build_blas(a[0][0], bvh_kind),
+                             zip(desc.mesh_datas, files)))
     t_blas = time.perf_counter() - t0
 
     node_bytes = 80 if bvh_kind == 8 else 32
@@ -1020,7 +1053,7 @@ class _MitsubaWalker:
         if typ == "obj":
             path = os.path.join(self.base, _child_by_name(node, "filename").get("value").replace("\\", "/"))
             if path not in self.mesh_cache:
-                self.mesh_cache[path] = self.desc.add_mesh_data(load_obj(path))
+                self.mesh_cache[path] = self.desc.add_mesh_data(load_obj(path), source=path)
             return self.mesh_cache[path]
         m = _parse_transform_matrix(node)
         if typ == "rectangle":

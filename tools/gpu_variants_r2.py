@@ -36,8 +36,9 @@ for name, path in json.loads(sys.argv[1]).items():
     for mode in modes:
         try:
             env = dict(os.environ, PTB_LIB_PATH=os.path.join(ROOT, path.split("+")[0]))
-            if path.endswith("+woop"):
-                env["PTB_WOOP"] = "1"
+            for extra in path.split("+")[1:]:                 # "lib.so+woop", "lib.so+PTB_NODE_TEST_EXACT=1"
+                if extra == "woop": env["PTB_WOOP"] = "1"
+                elif "=" in extra: env[extra.split("=")[0]] = extra.split("=", 1)[1]
             out = subprocess.run([sys.executable, "-c", CHILD % (ROOT, ROOT), str(mode)], env=env, capture_output=True, text=True, timeout=240)
             line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
             print(name, line[0] if line else "FAILED " + out.stderr[-400:], flush=True)
