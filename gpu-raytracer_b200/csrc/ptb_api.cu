@@ -124,7 +124,6 @@ struct ptb_ctx {
     bool overlap_enabled = true;
     // static merge: identity-transform instances re-built into ONE CWBVH at upload (rebuild_static_merge)
     bool merge_enabled = true;
-    bool fast_nodes = getenv("PTB_NODE_TEST_EXACT") == nullptr;   // XU-free conservative node test in the default mode (k_trace8<.., FAST>)
     bool merge_spatial = true;
     bool half_nodes = true;                           // conservative packed-half node test outside the bit-exact mode (A/B: PTB_HALF_NODES=0)                        // merged BVH built with spatial splits (SBVH); false = plain full-sweep SAH
     std::vector<unsigned char> host_nodes;            // node array as uploaded by the host (for leaf walks)
@@ -292,8 +291,7 @@ __global__ void __launch_bounds__(1024) k_apply_uploads(const unsigned char* are
 template <typename K> static void preload(K kernel) { cudaFuncAttributes a; cudaFuncGetAttributes(&a, kernel); }
 static void preload_kernels() {
     preload(k_generate); preload(k_begin_pass); preload(k_fold_counters); preload(k_sort); preload(k_accumulate);
-    preload(k_trace8<false, false, false>); preload(k_trace8<true, false, false>); preload(k_trace8<false, true, false>); preload(k_trace8<true, true, false>);
-    preload(k_trace8<false, false, true>); preload(k_trace8<true, false, true>); preload(k_trace8<false, true, true>); preload(k_trace8<true, true, true>);
+    preload(k_trace8<false, false>); preload(k_trace8<true, false>); preload(k_trace8<false, true>); preload(k_trace8<true, true>);
     preload(k_trace2<false, false>); preload(k_trace2<true, false>); preload(k_trace2<false, true>); preload(k_trace2<true, true>);
     preload(k_shade<BSDFDiffuse>); preload(k_shade<BSDFPlastic>); preload(k_shade<BSDFDielectric>); preload(k_shade<BSDFConductor>);
     preload(k_bin_count<false>); preload(k_bin_count<true>); preload(k_bin_scatter<false>); preload(k_bin_scatter<true>);
@@ -329,7 +327,6 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     memset(&F, 0, sizeof(F));
     F.width = width; F.height = height;
     F.rank = rank; F.world = world; F.band_rows = band_rows;
-    F.byte_magic = 0x47000000u;
 
     // defaults of GPUConfig (Common.h:39-67)
     F.config.reconstruction_filter = 2; F.config.aov_mask = 1u; F.config.num_bounces = 10;
@@ -352,14 +349,10 @@ extern "C" int ptb_create(ptb_ctx** out, int device, int width, int height, int 
     { int fe = allocate_film(ctx); if (fe) { ptb_destroy(ctx); return fe; } }
 
     preload_kernels();
-    CKC(cudaFuncSetAttribute(k_trace8<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CKC(cudaFuncSetAttribute(k_trace8<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CKC(cudaFuncSetAttribute(k_trace8<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CKC(cudaStreamSynchronize(ctx->stream));
     *out = ctx;
     return 0;
@@ -984,14 +977,8 @@ static size_t trace8_smem() { return 16 + (size_t)PTB_TLAS_STAGE_MAX_NODES * 80 
 
 template <bool SHADOW>
 static void launch_trace8(ptb_ctx* ctx, const Frame& F, int grid, cudaStream_t st, int bounce, const unsigned* order) {
-    const bool fast = ctx->merge_enabled && ctx->fast_nodes;      // strict mode keeps the reference's node arithmetic
-    if (fast) {
-        if (ctx->stats_mode) k_trace8<SHADOW, true, true><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order);
-        else                 k_trace8<SHADOW, false, true><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order);
-    } else {
-        if (ctx->stats_mode) k_trace8<SHADOW, true, false><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order);
-        else                 k_trace8<SHADOW, false, false><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order);
-    }
+    if (ctx->stats_mode) k_trace8<SHADOW, true><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order);
+    else                 k_trace8<SHADOW, false><<<grid, PTB_TRACE_BLOCK, trace8_smem(), st>>>(F, bounce, order);
 }
 
 // One wave: `samples` consecutive passes (first_sample ...) through the whole pipeline.  The role of one or several

@@ -272,60 +272,6 @@ PTB_DI unsigned cwbvh_node_intersect(const Ray& ray, unsigned oct_inv4, float ma
     return hit_mask;
 }
 
-// The same test for the default (static-merge) mode, where results are held to <= 1e-4 instead of bit equality: no XU-pipe
-// instruction at all.  ncu (profiles/r1_trace8_wave9_ncu.csv) shows the XU pipe as the busiest unit of the exact test (84 % on primary
-// rays: 32 I2F.U8 + 3 MUFU.RCP per node at a quarter of the FMA rate).  Here
-//   * 1 / d is computed once per ray (inv_d), not per node;
-//   * a quantised byte b becomes the float 32768 + b with ONE PRMT (the byte lands on mantissa bits 8..15 of 0x47000000), and the
-//     bias is folded into the FFMA's addend:  b * A + O  ==  (32768 + b) * A + (O - 32768 A)   with  A = 2^e / d,  O = (p - o) / d;
-//   * the addend B = fma(-32768, A, O) carries one rounding (<= 2^-24 |B|); the entry side uses B - 2^-22 |B| and the exit side
-//     B + 2^-22 |B|, so that a child the exact arithmetic accepts is never culled (the box grows by <= 2^-7 of one quantisation step
-//     plus 2^-22 of the node's distance: node visits per ray are unchanged to three digits).
-// A conservative test changes only the order in which equal-distance hits are met, never the closest hit itself.
-PTB_DI unsigned cwbvh_node_intersect_fast(float3 o, float3 inv_d, unsigned oct_inv4, float max_distance, unsigned magic, float4 n0, float4 n1, float4 n2, float4 n3, float4 n4) {
-    unsigned e_imask = __float_as_uint(n0.w);
-    float ax = __uint_as_float(byte_of(e_imask, 0) << 23) * inv_d.x;
-    float ay = __uint_as_float(byte_of(e_imask, 1) << 23) * inv_d.y;
-    float az = __uint_as_float(byte_of(e_imask, 2) << 23) * inv_d.z;
-    float bx = fmaf(-32768.0f, ax, (n0.x - o.x) * inv_d.x);
-    float by = fmaf(-32768.0f, ay, (n0.y - o.y) * inv_d.y);
-    float bz = fmaf(-32768.0f, az, (n0.z - o.z) * inv_d.z);
-    const float k = 2.384185791015625e-07f;      // 2^-22
-    float blx = fmaf(-k, fabsf(bx), bx), bhx = fmaf(k, fabsf(bx), bx);
-    float bly = fmaf(-k, fabsf(by), by), bhy = fmaf(k, fabsf(by), by);
-    float blz = fmaf(-k, fabsf(bz), bz), bhz = fmaf(k, fabsf(bz), bz);
-    const bool nx = !(oct_inv4 & 0x04u), ny = !(oct_inv4 & 0x02u), nz = !(oct_inv4 & 0x01u);     // direction sign bits (ray_octant_inv4)
-    unsigned hit_mask = 0;
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        unsigned meta4 = __float_as_uint(i == 0 ? n1.z : n1.w);
-        unsigned is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        unsigned inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-        unsigned bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-        unsigned child_bits4 = (meta4 >> 5) & 0x07070707u;
-        unsigned qlx = __float_as_uint(i == 0 ? n2.x : n2.y), qhx = __float_as_uint(i == 0 ? n2.z : n2.w);
-        unsigned qly = __float_as_uint(i == 0 ? n3.x : n3.y), qhy = __float_as_uint(i == 0 ? n3.z : n3.w);
-        unsigned qlz = __float_as_uint(i == 0 ? n4.x : n4.y), qhz = __float_as_uint(i == 0 ? n4.z : n4.w);
-        unsigned x_min = nx ? qhx : qlx, x_max = nx ? qlx : qhx;
-        unsigned y_min = ny ? qhy : qly, y_max = ny ? qly : qhy;
-        unsigned z_min = nz ? qhz : qlz, z_max = nz ? qlz : qhz;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const unsigned sel = 0x7604u | unsigned(j << 4);          // {0x47, 0x00, byte j, 0x00} = 32768 + byte j
-            float tx0 = fmaf(__uint_as_float(__byte_perm(x_min, magic, sel)), ax, blx);
-            float ty0 = fmaf(__uint_as_float(__byte_perm(y_min, magic, sel)), ay, bly);
-            float tz0 = fmaf(__uint_as_float(__byte_perm(z_min, magic, sel)), az, blz);
-            float tx1 = fmaf(__uint_as_float(__byte_perm(x_max, magic, sel)), ax, bhx);
-            float ty1 = fmaf(__uint_as_float(__byte_perm(y_max, magic, sel)), ay, bhy);
-            float tz1 = fmaf(__uint_as_float(__byte_perm(z_max, magic, sel)), az, bhz);
-            float tmin = imax3(tx0, ty0, fmaxf(tz0, 0.0f));
-            float tmax = imin3(tx1, ty1, fminf(tz1, max_distance));
-            if (tmin <= tmax) hit_mask |= byte_of(child_bits4, j) << byte_of(bit_index4, j);
-        }
-    }
-    return hit_mask;
-}
-
 // ------------------------------------------------------------------------------------------ pixel word: pixel | slot << pix_bits | flags
 PTB_DI int word_pixel(const Frame& P, unsigned w) { return int(w & ((1u << P.pix_bits) - 1u)); }
 PTB_DI int word_slot(const Frame& P, unsigned w) { return int((w & ~PTB_FLAGS_ALL) >> P.pix_bits); }

@@ -188,9 +188,7 @@ PTB_DI uint2 stack_pop(const TraceShared& S, const uint2* local, int& sp) {
 
 // STATS = true additionally counts node visits / triangle tests / instance transforms per ray kind (roofline accounting:
 // algorithmic bytes = 80 B per node + 48 B per triangle + 48 B per instance transform + the ray/hit streams).
-// FAST = the XU-free conservative node test (cwbvh_node_intersect_fast) with 1/d kept per ray: the default mode; the strict mode
-// (ptb_set_static_merge(0)) runs FAST = false, the reference's arithmetic bit for bit.
-template <bool SHADOW, bool STATS, bool FAST>
+template <bool SHADOW, bool STATS>
 __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace8(const __grid_constant__ Frame P, int bounce, const unsigned* __restrict__ order) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -216,7 +214,6 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
     uint2 cur = make_uint2(0, 0);
     int ray_index = 0;
     Ray ray; ray.o = f3(0.0f); ray.d = f3(1.0f);
-    float3 inv_d = f3(1.0f);
     unsigned oct4 = 0;
     Hit hit; hit.t = 0.0f; hit.u = hit.v = 0.0f; hit.mesh_id = 0; hit.triangle_id = PTB_INVALID;   // shadow rays: hit.t = max distance
     int tlas_sp = PTB_INVALID, mesh_id = 0;
@@ -240,7 +237,6 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                     else        { a = q.od0[ray_index];    b = q.od1[ray_index];    hit.t = PTB_INF; hit.triangle_id = PTB_INVALID; }
                     ray.o = f3(a.x, a.y, a.z); ray.d = f3(a.w, b.x, b.y);
                     oct4 = ray_octant_inv4(ray.d);
-                    if (FAST) inv_d = f3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
                     sp = 0; live = true;
                     if (P.flat_root >= 0) {
                         // merged static BVH first (it sets a tight hit.t early); the TLAS root waits on the stack for what is not merged
@@ -292,8 +288,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                         n0 = __ldg(n); n1 = __ldg(n + 1); n2 = __ldg(n + 2); n3 = __ldg(n + 3); n4 = __ldg(n + 4);
                     }
                     if (STATS) st_nodes++;
-                    unsigned hm = FAST ? cwbvh_node_intersect_fast(ray.o, inv_d, oct4, hit.t, P.byte_magic, n0, n1, n2, n3, n4)
-                                       : cwbvh_node_intersect(ray, oct4, hit.t, n0, n1, n2, n3, n4);
+                    unsigned hm = cwbvh_node_intersect(ray, oct4, hit.t, n0, n1, n2, n3, n4);
                     unsigned imask = byte_of(__float_as_uint(n0.w), 3);
                     cur.x = __float_as_uint(n1.x);
                     tri.x = __float_as_uint(n1.y);
@@ -323,7 +318,6 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                         ray.o = xform_pos(inv, ray.o);
                         ray.d = xform_dir(inv, ray.d);
                         oct4 = ray_octant_inv4(ray.d);
-                        if (FAST) inv_d = f3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
                         if (STATS) st_xf++;
                     }
                     cur = make_uint2(root & 0x3fffffffu, 0x80000000u);
@@ -377,7 +371,6 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
                                 float4 b = SHADOW ? P.sq.od1[ray_index] : q.od1[ray_index];
                                 ray.o = f3(a.x, a.y, a.z); ray.d = f3(a.w, b.x, b.y);
                                 oct4 = ray_octant_inv4(ray.d);
-                                if (FAST) inv_d = f3(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
                             }
                         }
                         cur = stack_pop(S, local_stack, sp);

@@ -219,7 +219,6 @@ struct Frame {
     // CWBVH (nodes appended to nodes8 at flat_root); rays walk that first and skip those instances in the TLAS.
     int           flat_root;          // node index of the merged BVH's root, -1 = none
     int           flat_all;           // every instance is merged: the TLAS is not traversed at all
-    unsigned      byte_magic;         // 0x47000000, passed at run time so that PRMT keeps it in its register operand and the selector immediate (cwbvh_node_intersect_fast)
     int           flat_node_count;
     const float4* flat_tris;          // 3 float4 per merged triangle: p0, e1, e2 (36 B) + original triangle id + merged slot
     const int*    flat_slot_instance; // merged slot -> current instance index (TLAS leaf order can change between frames)
