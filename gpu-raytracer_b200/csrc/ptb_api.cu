@@ -17,6 +17,9 @@
 #include "ptb_post.cuh"
 #include "../host/static_merge.h"
 #include "ptb_svgf.cuh"
+#include "ptb_refit.cuh"
+#include <unordered_map>
+#include <array>
 
 #define CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx_fail(ctx, #expr, (int)e__); return (int)e__; } } while (0)
 // inside ptb_create: a failure must not leak the half-built context
@@ -129,11 +132,14 @@ struct ptb_ctx {
     std::vector<unsigned char> host_nodes;            // node array as uploaded by the host (for leaf walks)
     std::vector<float4> host_tri_pos;                 // first 3 float4 of every triangle record
     std::vector<int> host_roots;                      // roots as last given by the host
+    std::unordered_map<unsigned, std::array<float, 6>> blas_root_boxes;    // BLAS root node -> its box in mesh space (ptb_refit_instances)
+    float* refit_scratch = nullptr;                   // device: local boxes | instance boxes | node boxes | done flags
     std::vector<int> merge_slot_root;                 // merged slot -> BLAS root (identity bit included)
     std::vector<int> merge_slot_instance;             // merged slot -> instance index in the current TLAS leaf order
     std::vector<int> merge_decided_roots;             // sorted roots of the identity instances the last merge decision (built, disabled or skipped) was taken on
     float4* merge_nodes = nullptr;                    // device: [host node array | merged nodes], owned
     float4* merge_tris = nullptr;
+    int     merge_ref_count = 0;                     // triangle references in the merged tree (>= triangles: spatial splits)
     float4* merge_woop = nullptr;                     // Woop maps of the merged references (ptb_set_intersector)
     int2*   merge_who = nullptr;
     int     intersector = PTB_INTERSECT_MT;
@@ -295,7 +301,7 @@ static void preload_kernels() {
     preload(k_trace2<false, false>); preload(k_trace2<true, false>); preload(k_trace2<false, true>); preload(k_trace2<true, true>);
     preload(k_shade<BSDFDiffuse>); preload(k_shade<BSDFPlastic>); preload(k_shade<BSDFDielectric>); preload(k_shade<BSDFConductor>);
     preload(k_bin_count<false>); preload(k_bin_count<true>); preload(k_bin_scatter<false>); preload(k_bin_scatter<true>);
-    preload(k_tap_primary_hits); preload(k_export_rows); preload(k_assemble_rows);
+    preload(k_tap_primary_hits); preload(k_refit_tlas); preload(k_retire_merged_slots); preload(k_export_rows); preload(k_assemble_rows);
     preload(k_exchange_wait); preload(k_svgf_push); preload(k_svgf_wait_arrivals); preload(k_svgf_push_display);
     preload(k_svgf_reproject); preload(k_svgf_variance); preload(k_svgf_atrous<0, false>); preload(k_svgf_atrous<1, false>); preload(k_svgf_atrous<2, false>); preload(k_svgf_atrous<1, true>); preload(k_svgf_atrous<2, true>); preload(k_svgf_finalize); preload(k_taa); preload(k_taa_finalize);
     preload(k_clear_framebuffers); preload(k_apply_uploads); preload(k_present); preload(k_ambient_occlusion);
@@ -373,6 +379,7 @@ extern "C" void ptb_destroy(ptb_ctx* ctx) {
     if (ctx->merge_woop) cudaFree(ctx->merge_woop);
     if (ctx->merge_who) cudaFree(ctx->merge_who);
     if (ctx->merge_slot_instance_dev) cudaFree(ctx->merge_slot_instance_dev);
+    if (ctx->refit_scratch) cudaFree(ctx->refit_scratch);
     if (g_drv.ok) for (auto& t : ctx->textures) { if (t.tex) g_drv.TexObjectDestroy(t.tex); if (t.array) g_drv.MipmappedArrayDestroy(t.array); }
     if (ctx->F.sky_tex) cudaDestroyTextureObject(ctx->F.sky_tex);
     if (ctx->sky_array) cudaFreeArray(ctx->sky_array);
@@ -600,12 +607,19 @@ static int stage_upload(ptb_ctx* ctx, void* dst, const void* src, size_t bytes) 
     if (!bytes) return 0;
     const int c = ctx->stage_cur;
     const size_t padded = (bytes + 15) & ~size_t(15);
-    if (!ctx->stage_open || (bytes & 3) || (reinterpret_cast<size_t>(dst) & 3) || ctx->stage_segments == PTB_STAGE_MAX_SEGMENTS ||
-        ctx->stage_used + padded > ctx->stage_cap[c]) {                             // no arena / odd size / full: plain synchronous copy, in order
+    if (!ctx->stage_open || (bytes & 3) || (reinterpret_cast<size_t>(dst) & 3)) {      // no arena / odd size: plain synchronous copy, in order
         int fe = staging_flush(ctx); if (fe) return fe;
         CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         return 0;
+    }
+    if (ctx->stage_segments == PTB_STAGE_MAX_SEGMENTS || ctx->stage_used + padded > ctx->stage_cap[c]) {
+        // segment table or arena full: ship this arena and go on in the other one (stream order keeps the segments in order); the
+        // call stays asynchronous -- round 1 fell back to a blocking copy here
+        int fe = staging_flush(ctx); if (fe) return fe;
+        size_t want = ctx->stage_cap[c] > 2 * padded + 4096 ? ctx->stage_cap[c] : 2 * padded + 4096;
+        int be = staging_begin(ctx, want); if (be) return be;
+        return stage_upload(ctx, dst, src, bytes);
     }
     unsigned char* at = ctx->stage_mem[c] + ctx->stage_used;
     memcpy(at, src, bytes);
@@ -618,6 +632,15 @@ static int staging_end(ptb_ctx* ctx) {
     int fe = staging_flush(ctx);
     ctx->stage_open = false;
     return fe;
+}
+// Ship what is staged and keep staging in the OTHER arena: for work that must be enqueued between two groups of uploads of one call.
+// (Appending to the same pinned arena after a flush would rewrite its segment table while the flush's asynchronous copy may still be
+// pending.)
+static int staging_split(ptb_ctx* ctx) {
+    if (!ctx->stage_open) return 0;
+    const size_t cap = ctx->stage_cap[ctx->stage_cur];
+    int fe = staging_flush(ctx); if (fe) return fe;
+    return staging_begin(ctx, cap > PTB_STAGE_TABLE_BYTES ? cap - PTB_STAGE_TABLE_BYTES : 4096);
 }
 
 static void upload_roots(ptb_ctx* ctx, std::vector<int>& device_roots) {
@@ -661,7 +684,7 @@ static int rebuild_static_merge(ptb_ctx* ctx) {
     ctx->merge_slot_root.clear(); ctx->merge_slot_instance.clear();
     ctx->merge_decided_roots = identity_roots_sorted(ctx->host_roots);
     if (ctx->merge_nodes) { cudaFree(ctx->merge_nodes); ctx->merge_nodes = nullptr; }
-    if (ctx->merge_tris) { cudaFree(ctx->merge_tris); ctx->merge_tris = nullptr; }
+    if (ctx->merge_tris) { cudaFree(ctx->merge_tris); ctx->merge_tris = nullptr; ctx->merge_ref_count = 0; }
     if (ctx->merge_woop) { cudaFree(ctx->merge_woop); ctx->merge_woop = nullptr; }
     if (ctx->merge_who) { cudaFree(ctx->merge_who); ctx->merge_who = nullptr; }
     F.flat_woop = nullptr; F.flat_who = nullptr;
@@ -757,7 +780,7 @@ static int rebuild_static_merge(ptb_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));       // `bfs` and `flat` are host temporaries
     F.nodes8 = ctx->merge_nodes;
     F.flat_root = base; F.flat_node_count = nm; F.flat_all = (int)slots.size() == M ? 1 : 0;
-    F.flat_tris = ctx->merge_tris; F.flat_slot_instance = ctx->merge_slot_instance_dev;
+    F.flat_tris = ctx->merge_tris; F.flat_slot_instance = ctx->merge_slot_instance_dev; ctx->merge_ref_count = n_refs;
     F.flat_who = ctx->merge_who; F.flat_woop = ctx->intersector == PTB_INTERSECT_WOOP ? ctx->merge_woop : nullptr;
     upload_roots(ctx, device_roots);
     return upload_pruned_tlas(ctx);
@@ -790,10 +813,19 @@ static int apply_roots(ptb_ctx* ctx, const int32_t* roots, int mesh_count) {
         if (j == ident.size()) continue;                                                             // retire
         taken[j] = 1; slot_instance[k] = ident[j];
     }
+    bool newly_retired = false;
+    for (size_t k = 0; k < slot_instance.size(); k++) if (slot_instance[k] < 0 && ctx->merge_slot_instance[k] >= 0) newly_retired = true;
     ctx->merge_slot_instance = slot_instance;
     std::vector<int> device_roots = ctx->host_roots;
     for (int i : slot_instance) if (i >= 0) device_roots[i] = int((unsigned)device_roots[i] | PTB_ROOT_MERGED);
     upload_roots(ctx, device_roots);
+    if (newly_retired && ctx->merge_tris && ctx->merge_ref_count > 0) {
+        // the slot table must be on the device before the records are poisoned; still no host <-> device synchronisation
+        int fe = staging_split(ctx); if (fe) return fe;
+        k_retire_merged_slots<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->merge_tris, ctx->merge_woop, ctx->merge_who, ctx->merge_ref_count, ctx->merge_slot_instance_dev);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
     return upload_pruned_tlas(ctx);
 }
 
@@ -926,6 +958,27 @@ extern "C" int ptb_upload_scene(ptb_ctx* ctx, const ptb_scene* s) {
     e = create_float_texture(ctx, &ctx->sky_array, &F.sky_tex, s->sky, 4, s->sky_width, s->sky_height, 0, false); if (e) return e;
     F.sky_scale = s->sky_scale;
 
+    // mesh-space box of every BLAS root (what a TLAS refit moves around): union of the root's child boxes
+    for (int i = 0; i < s->mesh_count; i++) {
+        unsigned root = (unsigned)s->mesh_bvh_root_indices[i] & 0x3fffffffu;
+        if (ctx->blas_root_boxes.count(root)) continue;
+        std::array<float, 6> b = { 1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f };
+        if (s->bvh_kind == 8) {
+            const unsigned char* n = static_cast<const unsigned char*>(s->bvh_nodes) + (size_t)root * 80;
+            float p[3]; memcpy(p, n, 12);
+            for (int k = 0; k < 8; k++) {
+                if (!n[24 + k]) continue;
+                for (int a = 0; a < 3; a++) {
+                    unsigned eb = (unsigned)n[12 + a] << 23; float scale; memcpy(&scale, &eb, 4);
+                    float lo = p[a] + scale * (float)n[32 + 16 * a + k], hi = p[a] + scale * (float)n[40 + 16 * a + k];
+                    b[a] = lo < b[a] ? lo : b[a]; b[3 + a] = hi > b[3 + a] ? hi : b[3 + a];
+                }
+            }
+        } else {
+            memcpy(b.data(), static_cast<const unsigned char*>(s->bvh_nodes) + (size_t)root * 32, 24);
+        }
+        ctx->blas_root_boxes[root] = b;
+    }
     ctx->has_scene = true;
     ctx->host_roots.assign(s->mesh_bvh_root_indices, s->mesh_bvh_root_indices + s->mesh_count);
     e = rebuild_static_merge(ctx); if (e) return e;
@@ -960,6 +1013,63 @@ extern "C" int ptb_update_instances(ptb_ctx* ctx, const void* tlas_nodes, int tl
     if (xf_prev) se |= stage_upload(ctx, (void*)F.mesh_transforms_prev, xf_prev, 48 * (size_t)mesh_count);
     if (se) return se;
     return staging_end(ctx);        // asynchronous: the copies run behind whatever the stream is still rendering
+}
+
+// TLAS refit on the device (ptb_refit.cuh): new transforms, same topology, no host BVH work and no host <-> device synchronisation.
+static bool is_identity_3x4(const float* m) {
+    static const float I[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+    return memcmp(m, I, sizeof(I)) == 0;
+}
+extern "C" int ptb_refit_instances(ptb_ctx* ctx, const float* xf, const float* xf_inv, const float* xf_prev) {
+    if (!ctx || !ctx->has_scene) return PTB_E_NOSCENE;
+    if (!xf || !xf_inv) return PTB_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    Frame& F = ctx->F;
+    const int M = ctx->mesh_capacity;
+    const int n_tlas = ctx->bvh_kind == 8 ? F.tlas_nodes : (2 * M < ctx->node_count ? 2 * M : ctx->node_count);
+    if (M <= 0 || n_tlas <= 0) return PTB_E_STATE;
+    // an instance that leaves (or returns to) the identity changes how it is traced: the ray transform is skipped for identity
+    // instances (root bit 31), and a moving instance must leave the merged static BVH (its slot is retired, apply_roots)
+    std::vector<int> roots = ctx->host_roots;
+    bool flags_changed = false;
+    std::vector<float> local((size_t)M * 6);
+    for (int i = 0; i < M; i++) {
+        unsigned r = (unsigned)roots[i], nr = is_identity_3x4(xf + 12 * (size_t)i) ? (r | PTB_ROOT_IDENTITY) : (r & ~PTB_ROOT_IDENTITY);
+        if (nr != r) { roots[i] = (int)nr; flags_changed = true; }
+        auto it = ctx->blas_root_boxes.find(r & 0x3fffffffu);
+        if (it == ctx->blas_root_boxes.end()) return PTB_E_STATE;
+        memcpy(&local[(size_t)i * 6], it->second.data(), 24);
+    }
+    const size_t node_slots = (size_t)(2 * M > n_tlas ? 2 * M : n_tlas);
+    if (!ctx->refit_scratch) CK(cudaMalloc(reinterpret_cast<void**>(&ctx->refit_scratch), ((size_t)M * 12 + node_slots * 7) * sizeof(float)));
+    float* d_local = ctx->refit_scratch; float* d_inst = d_local + (size_t)M * 6; float* d_node = d_inst + (size_t)M * 6;
+    int* d_done = reinterpret_cast<int*>(d_node + node_slots * 6);
+    // Integrator::update keeps last frame's transform for the motion vectors (Mesh::transform_prev).  Enqueued before anything is staged:
+    // the staged uploads of this call land with ONE flush at the end (a flush in the middle of a call would let the host overwrite the
+    // segment table of the pinned arena while its asynchronous copy may still be pending)
+    if (!xf_prev) CK(cudaMemcpyAsync((void*)F.mesh_transforms_prev, F.mesh_transforms, 48 * (size_t)M, cudaMemcpyDeviceToDevice, ctx->stream));
+    { int se = staging_begin(ctx, (size_t)M * (3 * 48 + 24 + 8) + (size_t)n_tlas * 80 + 8192); if (se) return se; }
+    if (flags_changed) { int re = apply_roots(ctx, roots.data(), M); if (re) return re; }
+    int se = stage_upload(ctx, (void*)F.mesh_transforms, xf, 48 * (size_t)M);
+    se |= stage_upload(ctx, (void*)F.mesh_transforms_inv, xf_inv, 48 * (size_t)M);
+    if (xf_prev) se |= stage_upload(ctx, (void*)F.mesh_transforms_prev, xf_prev, 48 * (size_t)M);
+    se |= stage_upload(ctx, d_local, local.data(), 24 * (size_t)M);
+    if (se) return se;
+    { int fe = staging_end(ctx); if (fe) return fe; }
+    RefitArgs A;
+    A.node_count = n_tlas; A.kind = ctx->bvh_kind; A.instance_count = M; A.local_boxes = d_local; A.transforms = F.mesh_transforms;
+    A.instance_boxes = d_inst; A.node_boxes = d_node; A.done = d_done;
+    // every copy of the TLAS a ray may walk: the array in use (the pruned copy next to the merged BVH, or the uploaded one) and, when
+    // they differ, the uploaded array the strict mode falls back to
+    float4* in_use = const_cast<float4*>(ctx->bvh_kind == 8 ? F.nodes8 : F.nodes2);
+    A.nodes = in_use;
+    k_refit_tlas<<<1, 1024, 0, ctx->stream>>>(A); ctx->launches++;
+    if (ctx->bvh_kind == 8 && ctx->uploaded_nodes && ctx->uploaded_nodes != F.nodes8) {
+        A.nodes = const_cast<float4*>(ctx->uploaded_nodes);
+        k_refit_tlas<<<1, 1024, 0, ctx->stream>>>(A); ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------- render
@@ -1398,6 +1508,15 @@ extern "C" int ptb_debug_read(ptb_ctx* ctx, int which, void* host_dst, int64_t b
         size_t need = (size_t)F.pitch * F.height * elem;
         if (!src[which - 10] || (size_t)bytes < need) return PTB_E_BADARG;
         CK(cudaMemcpyAsync(host_dst, src[which - 10], need, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    if (which == 3) {   // the TLAS the rays walk (front of the node array in use), e.g. after ptb_refit_instances
+        const size_t node_bytes = ctx->bvh_kind == 8 ? 80 : 32;
+        const int n = ctx->bvh_kind == 8 ? ctx->F.tlas_nodes : (2 * ctx->mesh_capacity < ctx->node_count ? 2 * ctx->mesh_capacity : ctx->node_count);
+        const void* src = ctx->bvh_kind == 8 ? (const void*)ctx->F.nodes8 : (const void*)ctx->F.nodes2;
+        if (!src || (size_t)bytes < node_bytes * (size_t)n) return PTB_E_BADARG;
+        CK(cudaMemcpyAsync(host_dst, src, node_bytes * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         return 0;
     }

@@ -115,7 +115,9 @@ PTB_DI TriPos load_tri_pos(const Frame& P, int id) {
     TriPos r; r.p0 = f3(a.x, a.y, a.z); r.e1 = f3(a.w, b.x, b.y); r.e2 = f3(b.z, b.w, c.x);
     return r;
 }
-// merged static BVH: compact 48-byte records, remap in the spare words
+// merged static BVH: compact 48-byte records, remap in the spare words.  A slot whose instance has started moving is RETIRED by
+// poisoning its records once (k_retire_merged_slots: p0.x = NaN, so u is NaN and every comparison of the test fails) -- the
+// triangle tests themselves carry no retirement check (a per-hit table lookup here cost 3.7 % of the frame, 27.05 -> 28.05 ms).
 PTB_DI TriPos load_tri_pos_flat(const Frame& P, int id, float4& c) {
     const float4* t = P.flat_tris + 3 * size_t(id);
     float4 a = __ldg(t), b = __ldg(t + 1); c = __ldg(t + 2);
@@ -168,9 +170,7 @@ PTB_DI void intersect_triangle(const Frame& P, int mesh_id, int tri_id, const Ra
         float t, u, v;
         if (woop_test(P, tri_id, ray, hit.t, t, u, v)) {
             int2 who = __ldg(P.flat_who + tri_id);
-            if (__ldg(P.flat_slot_instance + who.y) >= 0) {       // slot retired: its instance moved out of the merged tree (ptb_update_instances)
-                hit.t = t; hit.u = u; hit.v = v; hit.mesh_id = -(2 + who.y); hit.triangle_id = who.x;
-            }
+            hit.t = t; hit.u = u; hit.v = v; hit.mesh_id = -(2 + who.y); hit.triangle_id = who.x;
         }
         return;
     }
@@ -186,10 +186,7 @@ PTB_DI void intersect_triangle(const Frame& P, int mesh_id, int tri_id, const Ra
         float v = f * dot(ray.d, q);
         if (v >= 0.0f && u + v <= 1.0f) {
             float t = f * dot(tr.e2, q);
-            if (t > 0.0f && t < hit.t) {
-                // merged tree: a slot whose instance has since started moving is retired, its triangles no longer count
-                if (!flat || __ldg(P.flat_slot_instance + __float_as_int(c.z)) >= 0) { hit.t = t; hit.u = u; hit.v = v; hit.mesh_id = mesh_id; hit.triangle_id = tri_id; }
-            }
+            if (t > 0.0f && t < hit.t) { hit.t = t; hit.u = u; hit.v = v; hit.mesh_id = mesh_id; hit.triangle_id = tri_id; }
         }
     }
 }
@@ -199,7 +196,7 @@ PTB_DI bool occludes_triangle(const Frame& P, int mesh_id, int tri_id, const Ray
     const bool flat = mesh_id == PTB_FLAT_MESH;
     if (flat && P.flat_woop) {
         float t, u, v;
-        return woop_test(P, tri_id, ray, max_distance, t, u, v) && __ldg(P.flat_slot_instance + __ldg(P.flat_who + tri_id).y) >= 0;
+        return woop_test(P, tri_id, ray, max_distance, t, u, v);
     }
     TriPos tr = flat ? load_tri_pos_flat(P, tri_id, c) : load_tri_pos(P, tri_id);
     float3 h = cross(ray.d, tr.e2);
@@ -212,7 +209,7 @@ PTB_DI bool occludes_triangle(const Frame& P, int mesh_id, int tri_id, const Ray
         float v = f * dot(ray.d, q);
         if (v >= 0.0f && u + v <= 1.0f) {
             float t = f * dot(tr.e2, q);
-            if (t > 0.0f && t < max_distance) return !flat || __ldg(P.flat_slot_instance + __float_as_int(c.z)) >= 0;
+            if (t > 0.0f && t < max_distance) return true;
         }
     }
     return false;

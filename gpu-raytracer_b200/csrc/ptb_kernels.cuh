@@ -385,6 +385,20 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
     }
 }
 
+// Retirement of merged slots (ptb_update_instances / ptb_refit_instances: an identity instance started moving).  Every triangle record of
+// the merged tree whose slot maps to no instance any more is made unhittable: Moeller-Trumbore record p0.x = NaN (s = o - p0 is NaN,
+// u is NaN, `u >= 0` fails), Woop record row 2 = NaN (t is NaN, `t > 0` fails).  Runs once per retirement, not per frame.
+__global__ void __launch_bounds__(256) k_retire_merged_slots(float4* flat_tris, float4* flat_woop, const int2* flat_who, int n_refs, const int* slot_instance) {
+    const float nan = __int_as_float(0x7fc00000);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_refs; i += gridDim.x * blockDim.x) {
+        int slot = __float_as_int(flat_tris[3 * size_t(i) + 2].z);
+        if (slot_instance[slot] >= 0) continue;
+        flat_tris[3 * size_t(i)].x = nan;
+        if (flat_woop) flat_woop[3 * size_t(i) + 2] = make_float4(nan, nan, nan, nan);
+    }
+    (void)flat_who;
+}
+
 // ------------------------------------------------------------------------------------------ binary BVH traversal (config 1)
 // Src/CUDA/Raytracing/BVH2.h:4-244: ordered descent by split axis, TLAS leaf = instance.
 PTB_DI bool node2_hit(float4 a, float4 b, const Ray& ray, float tmax) {

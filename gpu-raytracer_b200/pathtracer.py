@@ -68,7 +68,7 @@ class PtbTraversalStats(ctypes.Structure):
 
 
 # every symbol include/ptb.h declares (tests check the built library exports exactly these)
-ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_render", "ptb_reserve_wave", "ptb_set_ray_ordering", "ptb_set_static_merge", "ptb_set_integrator", "ptb_set_intersector", "ptb_resize", "ptb_render_frame",
+ABI_SYMBOLS = ["ptb_create", "ptb_destroy", "ptb_upload_scene", "ptb_set_config", "ptb_set_camera", "ptb_update_instances", "ptb_refit_instances", "ptb_render", "ptb_reserve_wave", "ptb_set_ray_ordering", "ptb_set_static_merge", "ptb_set_integrator", "ptb_set_intersector", "ptb_resize", "ptb_render_frame",
                "ptb_measure_traversal", "ptb_sync", "ptb_get_aov", "ptb_get_display", "ptb_present", "ptb_download", "ptb_get_ray_stats", "ptb_set_pixel_query", "ptb_get_pixel_query", "ptb_get_stream", "ptb_export_rows",
                "ptb_assemble_rows", "ptb_exchange_create", "ptb_exchange_connect", "ptb_exchange_connect_ipc", "ptb_exchange_frame", "ptb_exchange_disconnect", "ptb_debug_read", "ptb_launch_count", "ptb_set_timing", "ptb_get_stage_ms", "ptb_stage_name",
                "ptb_error_string"]
@@ -89,6 +89,7 @@ def lib():
         l.ptb_set_config.argtypes = [vp, ctypes.POINTER(PtbConfig)]
         l.ptb_set_camera.argtypes = [vp, ctypes.POINTER(PtbCamera), vp, vp]
         l.ptb_update_instances.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
+        l.ptb_refit_instances.argtypes = [vp, vp, vp, vp]
         l.ptb_render.argtypes = [vp, ci]
         l.ptb_render_frame.argtypes = [vp, ci, ci]
         l.ptb_reserve_wave.argtypes = [vp, ci]
@@ -344,6 +345,19 @@ class Pathtracer:
         """include/ptb.h: ptb_set_static_merge (identity-transform instances traced through one merged CWBVH)."""
         _check(lib().ptb_set_static_merge(self._ctx, int(enabled)), "ptb_set_static_merge")     # False/0 off, True/1 SBVH, 2 plain SAH
 
+    def refit_instances(self, transforms, transforms_inv, transforms_prev=None):
+        """Moving instances without a host TLAS rebuild (ptb_refit_instances): [mesh_count, 12] float32 object-to-world and
+        world-to-object matrices in this context's table order (scene.instance_transforms(desc, blob["instance_order"])).
+        The TLAS boxes are refitted on the device; accumulation restarts."""
+        xf = np.ascontiguousarray(transforms, dtype=np.float32); xi = np.ascontiguousarray(transforms_inv, dtype=np.float32)
+        xp = None if transforms_prev is None else np.ascontiguousarray(transforms_prev, dtype=np.float32)
+        if xf.size != xi.size or (xp is not None and xp.size != xf.size):
+            raise ValueError("transform tables differ in size")
+        _check(lib().ptb_refit_instances(self._ctx, ctypes.c_void_p(xf.ctypes.data), ctypes.c_void_p(xi.ctypes.data),
+                                         ctypes.c_void_p(xp.ctypes.data) if xp is not None else None), "ptb_refit_instances")
+        if not self.gpu_config.enable_svgf:
+            self.sample_index = 0            # like a moved camera: the accumulator starts over (Integrator.cpp:443-452)
+
     def resize(self, blob):
         """Pathtracer::resize_free + resize_init (Pathtracer.cpp:255-314): same scene, the film size and camera block of `blob`
         (scene.retarget_blob); accumulation restarts."""
@@ -433,6 +447,12 @@ class Pathtracer:
         else:
             out = np.empty((self.screen_height, self.screen_pitch, 4), dtype=np.float32)
         _check(lib().ptb_debug_read(self._ctx, which, out.ctypes.data, out.nbytes), "ptb_debug_read")
+        return out
+
+    def tlas_nodes(self, node_count, node_bytes=80):
+        """The TLAS the rays currently walk (front of the device node array), e.g. after refit_instances: uint8 [node_count, node_bytes]."""
+        out = np.empty((int(node_count), int(node_bytes)), dtype=np.uint8)
+        _check(lib().ptb_debug_read(self._ctx, 3, out.ctypes.data, out.nbytes), "ptb_debug_read")
         return out
 
     def lut_contents(self):

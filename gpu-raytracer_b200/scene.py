@@ -673,6 +673,67 @@ def retarget_blob(blob, width, height, forward=None, fov=None):
     return out
 
 
+def instance_transforms(desc, order=None):
+    """3x4 object-to-world and world-to-object matrices of the instances (Mesh::update, Src/Renderer/Mesh.cpp:7-15), [M, 12] float32 each;
+    `order` (e.g. blob["instance_order"]) permutes them into a context's table order -- what Pathtracer.refit_instances expects."""
+    xf, xf_inv = [], []
+    for inst in desc.instances:
+        T = m_translate(inst.position) @ m_rotation(inst.rotation) @ m_scale(inst.scale)
+        Ti = m_scale(1.0 / inst.scale) @ m_rotation(q_conj(inst.rotation)) @ m_translate(-inst.position)
+        xf.append(T[:3, :].astype(f32).reshape(-1)); xf_inv.append(Ti[:3, :].astype(f32).reshape(-1))
+    xf, xf_inv = np.array(xf, dtype=f32), np.array(xf_inv, dtype=f32)
+    if order is not None:
+        xf, xf_inv = xf[np.asarray(order)], xf_inv[np.asarray(order)]
+    return np.ascontiguousarray(xf), np.ascontiguousarray(xf_inv)
+
+
+def check_tlas8(nodes, instance_boxes):
+    """Host-side validation of a CWBVH TLAS (uint8 [n, 80]) against world boxes of the instances ([M, 6], table order): every
+    instance must lie inside the de-quantised box of the leaf slot that references it, and every internal child's slot box must
+    contain the union of everything below it.  Returns (number of instances reached, largest overhang found -- 0 for a valid tree,
+    mean slack of the leaf slot boxes relative to the instance boxes)."""
+    nodes = np.asarray(nodes, dtype=np.uint8).reshape(-1, 80)
+    boxes = np.asarray(instance_boxes, dtype=np.float64).reshape(-1, 6)
+    worst, reached, slack = [0.0], [0], []
+
+    def slot_box(n, k):
+        p = n[:12].view(np.float32).astype(np.float64)
+        sc = np.array([np.array([int(n[12 + a]) << 23], dtype=np.uint32).view(np.float32)[0] for a in range(3)], dtype=np.float64)
+        lo = np.array([p[a] + sc[a] * n[32 + 16 * a + k] for a in range(3)]); hi = np.array([p[a] + sc[a] * n[40 + 16 * a + k] for a in range(3)])
+        return lo, hi
+
+    def walk(ni):
+        n = nodes[ni]
+        imask = int(n[15]); base_child = int(n[16:20].view(np.uint32)[0]); base_inst = int(n[20:24].view(np.uint32)[0])
+        lo_all, hi_all = np.full(3, np.inf), np.full(3, -np.inf)
+        internal = 0
+        for k in range(8):
+            meta = int(n[24 + k])
+            if imask & (1 << k):
+                child = base_child + internal; internal += 1
+                if not meta:
+                    continue
+                clo, chi = walk(child)
+            elif meta:
+                clo, chi = np.full(3, np.inf), np.full(3, -np.inf)
+                for t in range(bin(meta >> 5).count("1")):
+                    b = boxes[base_inst + (meta & 31) + t]; reached[0] += 1
+                    clo = np.minimum(clo, b[:3]); chi = np.maximum(chi, b[3:])
+            else:
+                continue
+            if not np.all(clo <= chi):
+                continue
+            lo, hi = slot_box(n, k)
+            worst[0] = max(worst[0], float(np.max(lo - clo)), float(np.max(chi - hi)))
+            if not (imask & (1 << k)):
+                slack.append(float(np.mean((clo - lo) + (hi - chi))))
+            lo_all = np.minimum(lo_all, clo); hi_all = np.maximum(hi_all, chi)
+        return lo_all, hi_all
+
+    walk(0)
+    return reached[0], worst[0], float(np.mean(slack)) if slack else 0.0
+
+
 def pack_triangles(p, n, t):
     out = np.empty((p.shape[0], 24), dtype=f32)
     out[:, 0:3] = p[:, 0]; out[:, 3:6] = p[:, 1] - p[:, 0]; out[:, 6:9] = p[:, 2] - p[:, 0]

@@ -136,6 +136,13 @@ int  ptb_set_camera(ptb_ctx* ctx, const ptb_camera* camera, const float* view_pr
 int  ptb_update_instances(ptb_ctx* ctx, const void* tlas_nodes, int tlas_node_count, int mesh_count,
                           const int32_t* mesh_bvh_root_indices, const int32_t* mesh_material_ids,
                           const float* transforms, const float* transforms_inv, const float* transforms_prev);
+/* TLAS refit on the GPU (replaces the per-frame CPU rebuild of Integrator::build_tlas, Integrator.cpp:399-430,
+ * for instances that only move): new 3x4 transforms (mesh_count x 12 floats each, in the order of the last uploaded tables), same TLAS
+ * topology.  The device recomputes every instance box from its BLAS root box and re-quantises the TLAS nodes bottom-up in place
+ * (csrc/ptb_refit.cuh); no host BVH work, no host <-> device synchronisation.  transforms_prev may be NULL: the transforms in use become
+ * the previous ones (Mesh::transform_prev).  An instance whose transform stops being the identity leaves the merged static BVH (its
+ * slot is retired) and is traced through the TLAS from then on.  Closest hits equal those of a TLAS rebuilt on the host. */
+int  ptb_refit_instances(ptb_ctx* ctx, const float* transforms, const float* transforms_inv, const float* transforms_prev);
 /* Pathtracer::render() for one pass with the given sample_index (Pathtracer.cpp:738-855). Asynchronous on the ctx stream. */
 int  ptb_render(ptb_ctx* ctx, int sample_index);
 /* Replaces the reference's batching (BATCH_SIZE = 1080 x 720 pixels, Src/CUDA/Common.h:69-71; a blocking 4-KB upload between batches, Pathtracer.cpp:789-795):

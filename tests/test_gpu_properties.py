@@ -297,6 +297,72 @@ def test_static_merge_follows_instance_updates():
         assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
 
 
+@pytest.mark.parametrize("bvh_kind,merge", [(8, 1), (8, 0), (2, 0)])
+def test_tlas_refit_on_device_equals_host_rebuilt_tlas(bvh_kind, merge):
+    """ptb_refit_instances: instances move (translations, rotations, an identity instance starting to move, a lamp), the
+    TLAS keeps its topology and is refitted by k_refit_tlas on the device.  The frame must equal the one of a context that was given
+    the moved scene with a TLAS rebuilt on the host -- any valid BVH yields the same closest hits; only the order in which
+    equal-distance hits are met may differ, hence the tie allowance."""
+    import copy
+    d = scene.procedural_scene("atrium", seed=5, width=320, height=192, detail=0.5)
+    blob = scene.build_blob(d, bvh_kind, rng="fallback")
+    moved = copy.deepcopy(d)
+    for i, inst in enumerate(moved.instances):
+        if inst.name == "column" and i % 2:
+            inst.position = inst.position + np.array([0.6, 0.0, -0.4]); inst.rotation = scene.q_axis_angle((0, 1, 0), 0.2 * i)
+        elif inst.name == "curtain":
+            inst.position = inst.position + np.array([0.0, 0.5, 0.0])
+        elif inst.name == "floor":
+            inst.position = inst.position + np.array([0.0, -0.15, 0.0])          # identity -> moving: leaves the merged static BVH
+        elif inst.name == "lamp" and i % 2:
+            inst.position = inst.position + np.array([1.0, -0.5, 0.5])
+    rebuilt = scene.build_blob(moved, bvh_kind, rng="fallback")
+    cfg = pt.default_config(num_bounces=3)
+    want = pt.Pathtracer(rebuilt, config=cfg); want.set_static_merge(merge)
+    want.render_frames(3)
+    ref_img = want.get_aov(0); ref_albedo = None
+    want.close()
+
+    p = pt.Pathtracer(blob, config=cfg); p.set_static_merge(merge)
+    p.render_frames(2)                                                           # graphs, merged tree and pruned TLAS exist before the move
+    xf, xi = scene.instance_transforms(moved, blob["instance_order"])
+    p.refit_instances(xf, xi)
+    if bvh_kind == 8:
+        # the refitted TLAS itself, read back: every instance inside the slot box that references it, every internal slot box around
+        # everything below it (overhang 0), and about as tight as a TLAS built on the host for the moved scene
+        p.sync()
+        order = np.asarray(blob["instance_order"])
+        boxes = []
+        for j, i in enumerate(order):
+            inst = moved.instances[i]; pts = moved.mesh_datas[inst.mesh_data][0].reshape(-1, 3).astype(np.float64)
+            T = xf[j].reshape(3, 4).astype(np.float64); lo, hi = pts.min(0), pts.max(0); c, e = 0.5 * (lo + hi), 0.5 * (hi - lo)
+            nc = T[:, :3] @ c + T[:, 3]; ne = np.abs(T[:, :3]) @ e
+            boxes.append(np.concatenate([nc - ne, nc + ne]))
+        reached, overhang, slack = scene.check_tlas8(p.tlas_nodes(int(blob["tlas_node_count"])), np.array(boxes))
+        assert reached == len(order) and overhang <= 1e-5 and slack < 0.2, (reached, overhang, slack)
+    p.invalidated_gpu_config = True
+    p.render_frames(3)
+    got = p.get_aov(0)
+    # a second refit back to the start must restore the original picture (the blanked / retired bookkeeping survives round trips)
+    xf0, xi0 = scene.instance_transforms(d, blob["instance_order"])
+    p.refit_instances(xf0, xi0); p.invalidated_gpu_config = True
+    p.render_frames(3)
+    back = p.get_aov(0)
+    p.close()
+    fresh = pt.Pathtracer(blob, config=cfg); fresh.set_static_merge(merge); fresh.render_frames(3); orig = fresh.get_aov(0); fresh.close()
+
+    def close(a, b):
+        w = a.shape[1]
+        differ = np.any(a.view(np.uint32) != b.view(np.uint32), axis=-1).mean()
+        err = np.linalg.norm((a - b).astype(np.float64)) / max(np.linalg.norm(b.astype(np.float64)), 1e-30)
+        return differ, err
+    differ, err = close(got, ref_img)
+    assert differ <= 0.01 and err <= 1e-5, (differ, err)
+    differ, err = close(back, orig)
+    assert differ <= 0.01 and err <= 1e-5, (differ, err)
+    assert np.abs(got - orig).max() > 0.05                                       # the move is visible: the refit did something
+
+
 def _exchange_frame_host(p, like):
     import ctypes
     rt = ctypes.CDLL("libcudart.so.12")
