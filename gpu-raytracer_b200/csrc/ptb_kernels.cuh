@@ -556,15 +556,25 @@ PTB_DI void deposit(const Frame& P, int bounce, int px, float3 at_bounce0, float
     }
 }
 
-__global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, int bounce) {
+#ifndef PTB_SORT_MIN_BLOCKS
+#define PTB_SORT_MIN_BLOCKS 4
+#endif
+// one atomic per group of lanes that are active at the call site (divergent code: the rare medium-scatter emission of k_sort)
+PTB_DI int append_active(int* counter) {
+    unsigned act = __activemask();
+    unsigned lane = threadIdx.x & 31u;
+    int leader = __ffs(act) - 1, base = 0;
+    if (int(lane) == leader) base = atomicAdd(counter, __popc(act));
+    base = __shfl_sync(act, base, leader);
+    return base + __popc(act & ((1u << lane) - 1u));
+}
+__global__ void __launch_bounds__(256, PTB_SORT_MIN_BLOCKS) k_sort(const __grid_constant__ Frame P, int bounce) {
     const RayQueue& q = P.q[bounce & 1];
     const RayQueue& qn = P.q[(bounce + 1) & 1];
     const int count = P.counters->trace[bounce];
     const int rounded = (count + 31) & ~31;     // whole warps iterate together so the aggregated appends stay converged
     for (int index = blockIdx.x * blockDim.x + threadIdx.x; index < rounded; index += gridDim.x * blockDim.x) {
         int dest = -1;                            // material queue to join: 0..3, -1 = path ended (or scattered)
-        bool scatter = false;                     // medium scattering emits straight into the next trace queue
-        float4 sc_od0, sc_od1, sc_path; unsigned sc_pix = 0; int sc_medium = 0;
         if (index < count) {
             float4 a = q.od0[index], b = q.od1[index];
             float3 ray_direction = f3(a.w, b.x, b.y);
@@ -609,12 +619,14 @@ __global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, i
                                 cone_angle = P.camera.pixel_spread_angle;
                                 cone_width = P.camera.pixel_spread_angle * dist;
                             }
-                            scatter = true;
-                            sc_od0 = make_float4(org.x, org.y, org.z, dir_out.x);
-                            sc_od1 = make_float4(dir_out.y, dir_out.z, cone_angle, cone_width);
-                            sc_path = make_float4(throughput.x, throughput.y, throughput.z, 0.0f);
-                            sc_pix = (pf & ~PTB_FLAGS_ALL) | PTB_FLAG_INSIDE_MEDIUM;
-                            sc_medium = medium_id;
+                            // medium scattering emits straight into the next trace queue (rare: appended from inside the branch, so
+                            // that its 14 values are not live registers of the common path)
+                            int slot = append_active(&P.counters->trace[bounce + 1]);
+                            qn.od0[slot] = make_float4(org.x, org.y, org.z, dir_out.x);
+                            qn.od1[slot] = make_float4(dir_out.y, dir_out.z, cone_angle, cone_width);
+                            qn.path[slot] = make_float4(throughput.x, throughput.y, throughput.z, 0.0f);
+                            qn.pix[slot] = (pf & ~PTB_FLAGS_ALL) | PTB_FLAG_INSIDE_MEDIUM;
+                            qn.medium[slot] = medium_id;
                         }
                         ended = true;
                     } else {
@@ -683,10 +695,6 @@ __global__ void __launch_bounds__(256) k_sort(const __grid_constant__ Frame P, i
         for (int m = 0; m < 4; m++) {
             int slot = warp_append(&P.counters->mat[m][bounce], dest == m);
             if (dest == m) P.matq[m][slot] = index;
-        }
-        if (__any_sync(0xffffffffu, scatter)) {
-            int slot = warp_append(&P.counters->trace[bounce + 1], scatter);
-            if (scatter) { qn.od0[slot] = sc_od0; qn.od1[slot] = sc_od1; qn.path[slot] = sc_path; qn.pix[slot] = sc_pix; qn.medium[slot] = sc_medium; }
         }
     }
 }
