@@ -299,6 +299,7 @@ static void preload_kernels() {
     preload(k_generate); preload(k_begin_pass); preload(k_fold_counters); preload(k_sort); preload(k_accumulate);
     preload(k_trace8<false, false>); preload(k_trace8<true, false>); preload(k_trace8<false, true>); preload(k_trace8<true, true>);
     preload(k_trace2<false, false>); preload(k_trace2<true, false>); preload(k_trace2<false, true>); preload(k_trace2<true, true>);
+    preload(k_trace4<false, false>); preload(k_trace4<true, false>); preload(k_trace4<false, true>); preload(k_trace4<true, true>);
     preload(k_shade<BSDFDiffuse>); preload(k_shade<BSDFPlastic>); preload(k_shade<BSDFDielectric>); preload(k_shade<BSDFConductor>);
     preload(k_bin_count<false>); preload(k_bin_count<true>); preload(k_bin_scatter<false>); preload(k_bin_scatter<true>);
     preload(k_tap_primary_hits); preload(k_refit_tlas); preload(k_retire_merged_slots); preload(k_export_rows); preload(k_assemble_rows);
@@ -889,7 +890,7 @@ extern "C" int ptb_set_intersector(ptb_ctx* ctx, int kind) {
 extern "C" int ptb_upload_scene(ptb_ctx* ctx, const ptb_scene* s) {
     if (!ctx || !s) return PTB_E_BADARG;
     if (ctx->has_scene) return PTB_E_STATE;     // one scene per ctx (create a new ctx to switch scenes)
-    if (!s->triangles || !s->bvh_nodes || s->mesh_count <= 0 || (s->bvh_kind != 8 && s->bvh_kind != 2) || !s->pmj_samples || !s->blue_noise || !s->sky)
+    if (!s->triangles || !s->bvh_nodes || s->mesh_count <= 0 || (s->bvh_kind != 8 && s->bvh_kind != 4 && s->bvh_kind != 2) || !s->pmj_samples || !s->blue_noise || !s->sky)
         return PTB_E_BADARG;
     // layout convention of the node array (Integrator.cpp:113,252-277): TLAS in slots [0, 2 * mesh_count), every BLAS root behind it --
     // ptb_update_instances overwrites the front of the array and relies on it
@@ -905,6 +906,7 @@ extern "C" int ptb_upload_scene(ptb_ctx* ctx, const ptb_scene* s) {
     e |= dev_upload<float4>(ctx, &F.triangles, s->triangles, (size_t)s->triangle_count * 6);
     ctx->bvh_kind = s->bvh_kind; ctx->node_count = s->bvh_node_count;
     if (s->bvh_kind == 8) { e |= dev_upload<float4>(ctx, &F.nodes8, s->bvh_nodes, (size_t)s->bvh_node_count * 5); ctx->uploaded_nodes = F.nodes8; }
+    else if (s->bvh_kind == 4) e |= dev_upload<float4>(ctx, &F.nodes4, s->bvh_nodes, (size_t)s->bvh_node_count * 8);
     else                  e |= dev_upload<float4>(ctx, &F.nodes2, s->bvh_nodes, (size_t)s->bvh_node_count * 2);
     F.flat_root = -1;
     if (s->bvh_kind == 8) {
@@ -974,7 +976,7 @@ extern "C" int ptb_upload_scene(ptb_ctx* ctx, const ptb_scene* s) {
                     b[a] = lo < b[a] ? lo : b[a]; b[3 + a] = hi > b[3 + a] ? hi : b[3 + a];
                 }
             }
-        } else {
+        } else if (s->bvh_kind == 2) {
             memcpy(b.data(), static_cast<const unsigned char*>(s->bvh_nodes) + (size_t)root * 32, 24);
         }
         ctx->blas_root_boxes[root] = b;
@@ -994,8 +996,8 @@ extern "C" int ptb_update_instances(ptb_ctx* ctx, const void* tlas_nodes, int tl
     CK(cudaSetDevice(ctx->device));
     if (ctx->bvh_kind == 8 && ctx->F.tlas_nodes != tlas_node_count) drop_graphs(ctx);
     Frame& F = ctx->F;
-    size_t node_bytes = ctx->bvh_kind == 8 ? 80 : 32;
-    void* dst = ctx->bvh_kind == 8 ? (void*)F.nodes8 : (void*)F.nodes2;
+    size_t node_bytes = ctx->bvh_kind == 8 ? 80 : ctx->bvh_kind == 4 ? 128 : 32;
+    void* dst = ctx->bvh_kind == 8 ? (void*)F.nodes8 : ctx->bvh_kind == 4 ? (void*)F.nodes4 : (void*)F.nodes2;
     { int se = staging_begin(ctx, 3 * node_bytes * (size_t)tlas_node_count + (size_t)mesh_count * 192 + 4096); if (se) return se; }
     { int se = stage_upload(ctx, dst, tlas_nodes, node_bytes * tlas_node_count); if (se) return se; }
     if (ctx->bvh_kind == 8 && ctx->uploaded_nodes != F.nodes8)      // keep the un-merged copy current as well
@@ -1023,6 +1025,7 @@ static bool is_identity_3x4(const float* m) {
 extern "C" int ptb_refit_instances(ptb_ctx* ctx, const float* xf, const float* xf_inv, const float* xf_prev) {
     if (!ctx || !ctx->has_scene) return PTB_E_NOSCENE;
     if (!xf || !xf_inv) return PTB_E_BADARG;
+    if (ctx->bvh_kind == 4) return PTB_E_STATE;          // refit covers the CWBVH and the binary TLAS; a 4-wide TLAS is rebuilt on the host (ptb_update_instances)
     CK(cudaSetDevice(ctx->device));
     Frame& F = ctx->F;
     const int M = ctx->mesh_capacity;
@@ -1150,6 +1153,7 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
           k_bin_count<false><<<g1d, 256, 0, st>>>(F, bounce); k_bin_scatter<false><<<g1d, 256, 0, st>>>(F, bounce); ctx->launches += 2; }
         { StageTimer t(ctx, ST_TRACE);
           if (ctx->bvh_kind == 8) { launch_trace8<false>(ctx, F, gtrace, st, bounce, order_c); }
+          else if (ctx->bvh_kind == 4) { if (ctx->stats_mode) k_trace4<false, true><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce); else k_trace4<false, false><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce); }
           else if (ctx->stats_mode) k_trace2<false, true><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
           else                    k_trace2<false, false><<<gtrace, PTB_TRACE_BLOCK, 0, st>>>(F, bounce);
           ctx->launches++; }
@@ -1168,6 +1172,7 @@ static int render_wave(ptb_ctx* ctx, int first_sample, int samples, bool push = 
             cudaStream_t ss = st;
             if (overlap) { CK(cudaEventRecord(ctx->ev_fork, st)); CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0)); ss = ctx->side_stream; }
             if (ctx->bvh_kind == 8) { launch_trace8<true>(ctx, F, gtrace, ss, bounce, order_s); }
+            else if (ctx->bvh_kind == 4) { if (ctx->stats_mode) k_trace4<true, true><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce); else k_trace4<true, false><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce); }
             else if (ctx->stats_mode) k_trace2<true, true><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce);
             else                    k_trace2<true, false><<<gtrace, PTB_TRACE_BLOCK, 0, ss>>>(F, bounce);
             ctx->launches++;
@@ -1512,9 +1517,9 @@ extern "C" int ptb_debug_read(ptb_ctx* ctx, int which, void* host_dst, int64_t b
         return 0;
     }
     if (which == 3) {   // the TLAS the rays walk (front of the node array in use), e.g. after ptb_refit_instances
-        const size_t node_bytes = ctx->bvh_kind == 8 ? 80 : 32;
+        const size_t node_bytes = ctx->bvh_kind == 8 ? 80 : ctx->bvh_kind == 4 ? 128 : 32;
         const int n = ctx->bvh_kind == 8 ? ctx->F.tlas_nodes : (2 * ctx->mesh_capacity < ctx->node_count ? 2 * ctx->mesh_capacity : ctx->node_count);
-        const void* src = ctx->bvh_kind == 8 ? (const void*)ctx->F.nodes8 : (const void*)ctx->F.nodes2;
+        const void* src = ctx->bvh_kind == 8 ? (const void*)ctx->F.nodes8 : ctx->bvh_kind == 4 ? (const void*)ctx->F.nodes4 : (const void*)ctx->F.nodes2;
         if (!src || (size_t)bytes < node_bytes * (size_t)n) return PTB_E_BADARG;
         CK(cudaMemcpyAsync(host_dst, src, node_bytes * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));

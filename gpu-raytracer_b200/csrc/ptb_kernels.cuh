@@ -494,6 +494,122 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
     }
 }
 
+// ------------------------------------------------------------------------------------------ 4-wide BVH traversal (--bvh bvh4)
+// Src/CUDA/Raytracing/BVH4.h:4-295.  A stack entry names one child SLOT: (node index | slot << 30); popping it reads that slot's
+// (index, count): a leaf is intersected (or, at TLAS level, entered), an internal child has its four boxes tested and the hit ones pushed
+// far to near.  The order comes from the reference's trick: the slot number replaces the two low mantissa bits of t_near, and a three-pass
+// bubble sort orders the four tagged floats (descending, so the nearest is pushed last); both are replicated exactly, ties included.
+struct Quad4Hits { float t_near[4]; bool hit[4]; };
+PTB_DI Quad4Hits node4_intersect(const float4* n, const Ray& ray, float tmax) {
+    float4 lx = __ldg(n), ly = __ldg(n + 1), lz = __ldg(n + 2), hx = __ldg(n + 3), hy = __ldg(n + 4), hz = __ldg(n + 5);
+    float tx0[4] = { (lx.x - ray.o.x) / ray.d.x, (lx.y - ray.o.x) / ray.d.x, (lx.z - ray.o.x) / ray.d.x, (lx.w - ray.o.x) / ray.d.x };
+    float tx1[4] = { (hx.x - ray.o.x) / ray.d.x, (hx.y - ray.o.x) / ray.d.x, (hx.z - ray.o.x) / ray.d.x, (hx.w - ray.o.x) / ray.d.x };
+    float ty0[4] = { (ly.x - ray.o.y) / ray.d.y, (ly.y - ray.o.y) / ray.d.y, (ly.z - ray.o.y) / ray.d.y, (ly.w - ray.o.y) / ray.d.y };
+    float ty1[4] = { (hy.x - ray.o.y) / ray.d.y, (hy.y - ray.o.y) / ray.d.y, (hy.z - ray.o.y) / ray.d.y, (hy.w - ray.o.y) / ray.d.y };
+    float tz0[4] = { (lz.x - ray.o.z) / ray.d.z, (lz.y - ray.o.z) / ray.d.z, (lz.z - ray.o.z) / ray.d.z, (lz.w - ray.o.z) / ray.d.z };
+    float tz1[4] = { (hz.x - ray.o.z) / ray.d.z, (hz.y - ray.o.z) / ray.d.z, (hz.z - ray.o.z) / ray.d.z, (hz.w - ray.o.z) / ray.d.z };
+    Quad4Hits r;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        float tn = imin_max(tx0[c], tx1[c], imin_max(ty0[c], ty1[c], imin_max(tz0[c], tz1[c], 0.0f)));
+        float tf = imax_min(tx0[c], tx1[c], imax_min(ty0[c], ty1[c], imax_min(tz0[c], tz1[c], tmax)));
+        r.hit[c] = tn < tf;
+        r.t_near[c] = __uint_as_float((__float_as_uint(tn) & 0xfffffffcu) | unsigned(c));
+    }
+#pragma unroll
+    for (int i = 1; i < 4; i++) {
+#pragma unroll
+        for (int j = i - 1; j >= 0; j--) {
+            if (r.t_near[j] < r.t_near[j + 1]) { float t = r.t_near[j]; r.t_near[j] = r.t_near[j + 1]; r.t_near[j + 1] = t; }
+        }
+    }
+    return r;
+}
+
+template <bool SHADOW, bool STATS>
+__global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace4(const __grid_constant__ Frame P, int bounce) {
+    const int count = SHADOW ? P.counters->shadow[bounce] : P.counters->trace[bounce];
+    int* retired = SHADOW ? &P.counters->retired_shadow[bounce] : &P.counters->retired[bounce];
+    const RayQueue& q = P.q[bounce & 1];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned FULL = 0xffffffffu;
+    unsigned stack[PTB_STACK_TOTAL];
+    unsigned long long st_nodes = 0, st_tris = 0, st_xf = 0, st_rays = 0, st_miss = 0;
+    while (true) {
+        int base = 0;                                  // one ray per lane per round; the refill is warp-aggregated
+        if (lane == 0) base = atomicAdd(retired, 32);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= count) {
+            if (STATS) {
+                TraceStats* ts = P.trace_stats + (SHADOW ? 1 : 0);
+                atomicAdd(&ts->nodes, st_nodes); atomicAdd(&ts->triangles, st_tris); atomicAdd(&ts->instance_transforms, st_xf);
+                atomicAdd(&ts->rays, st_rays); atomicAdd(&ts->misses, st_miss);
+            }
+            return;
+        }
+        int ray_index = base + int(lane);
+        if (ray_index >= count) continue;
+        if (STATS) st_rays++;
+        float4 a = SHADOW ? P.sq.od0[ray_index] : q.od0[ray_index];
+        float4 b = SHADOW ? P.sq.od1[ray_index] : q.od1[ray_index];
+        Ray world; world.o = f3(a.x, a.y, a.z); world.d = f3(a.w, b.x, b.y);
+        Ray ray = world;
+        Hit hit; hit.t = SHADOW ? b.z : PTB_INF; hit.u = hit.v = 0.0f; hit.mesh_id = 0; hit.triangle_id = PTB_INVALID;
+        int sp = 0, tlas_sp = PTB_INVALID, mesh_id = 0;
+        bool identity = true, occluded = false;
+        stack[sp++] = 1u;                              // (node 1, slot 0): the entry slot, pointing at the TLAS root
+        while (sp > 0 && !occluded) {
+            if (sp == tlas_sp) { tlas_sp = PTB_INVALID; if (!identity) ray = world; }
+            unsigned packed = stack[--sp];
+            const float4* slots = P.nodes4 + 8 * size_t(packed & 0x3fffffffu) + 6;
+            float4 ic = __ldg(slots + ((packed >> 30) >> 1));                       // two (index, count) pairs per float4
+            int index = __float_as_int((packed >> 30) & 1u ? ic.z : ic.x), n = __float_as_int((packed >> 30) & 1u ? ic.w : ic.y);
+            if (n > 0) {
+                if (tlas_sp == PTB_INVALID) {
+                    tlas_sp = sp;
+                    mesh_id = index;
+                    unsigned root = unsigned(__ldg(P.mesh_roots + mesh_id));
+                    identity = (root >> 31) != 0;
+                    if (!identity) {
+                        Mat3x4 inv = load_mat(P.mesh_transforms_inv, mesh_id);
+                        ray.o = xform_pos(inv, ray.o); ray.d = xform_dir(inv, ray.d);
+                        if (STATS) st_xf++;
+                    }
+                    stack[sp++] = (root & 0x3fffffffu) + 1u;                        // the BLAS's own entry slot
+                } else {
+                    for (int t = index; t < index + n; t++) {
+                        if (STATS) st_tris++;
+                        if (SHADOW) { if (occludes_triangle(P, mesh_id, t, ray, hit.t)) { occluded = true; break; } }
+                        else intersect_triangle(P, mesh_id, t, ray, hit);
+                    }
+                }
+            } else {
+                if (STATS) st_nodes++;
+                Quad4Hits h = node4_intersect(P.nodes4 + 8 * size_t(index), ray, hit.t);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    unsigned id = __float_as_uint(h.t_near[i]) & 3u;
+                    bool take = id == 0 ? h.hit[0] : id == 1 ? h.hit[1] : id == 2 ? h.hit[2] : h.hit[3];
+                    if (take) stack[sp++] = (id << 30) | unsigned(index);
+                }
+            }
+        }
+        if (SHADOW) {
+            if (!occluded) {
+                if (STATS) st_miss++;
+                float4 ill = P.sq.illum[ray_index];
+                int px = word_fb_index(P, __float_as_uint(b.w));
+                float4 v = make_float4(ill.x, ill.y, ill.z, ill.w);
+                aov_add(P, PTB_AOV_RADIANCE, px, v);
+                if (bounce == 0) aov_set(P, PTB_AOV_RADIANCE_DIRECT, px, v);
+                else             aov_add(P, PTB_AOV_RADIANCE_INDIRECT, px, v);
+            }
+        } else {
+            q.hit[ray_index] = pack_hit(hit);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ SVGF g-buffers (SVGF.h:61-98)
 PTB_DI float2 oct_encode_normal(float3 n) {
     n /= (fabsf(n.x) + fabsf(n.y) + fabsf(n.z));

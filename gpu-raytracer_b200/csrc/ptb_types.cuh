@@ -184,6 +184,7 @@ struct Frame {
     const float4*        triangles;   // 6 float4 per triangle
     const float4*        nodes8;      // 5 float4 per CWBVH node
     const float4*        nodes2;      // 2 float4 per binary node
+    const float4*        nodes4;      // 8 float4 per 4-wide node (BVH.h:25-59): lo x,y,z / hi x,y,z of the four children, then 4 x (index, count)
     int                  tlas_nodes;  // nodes8 [0, tlas_nodes) are the TLAS
     const int*           mesh_roots;
     const int*           mesh_material_ids;

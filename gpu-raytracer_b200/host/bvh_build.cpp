@@ -201,6 +201,80 @@ struct SAHBuilder {
 struct BVH2 { std::vector<Node2> nodes; std::vector<int> indices; };
 struct BVH8 { std::vector<Node8> nodes; std::vector<int> indices; };
 
+// 128-byte 4-wide node (Src/BVH/BVH.h:25-59): child boxes as structure of arrays, then (index, count) per child.
+// count > 0: leaf (index = first primitive), count == 0: internal (index = node), count == -1: unused slot.
+struct Node4 {
+    float   lo_x[4], lo_y[4], lo_z[4], hi_x[4], hi_y[4], hi_z[4];
+    struct { int32_t index, count; } child[4];
+    int used() const { int n = 0; while (n < 4 && child[n].count != -1) n++; return n; }
+};
+static_assert(sizeof(Node4) == 128, "BVH4 node must be 128 bytes");
+struct BVH4 { std::vector<Node4> nodes; std::vector<int> indices; };
+
+// ---------------------------------------------------------------- BVH2 -> BVH4
+// The reference's 4-wide tree (Src/BVH/Converters/BVH4Converter.cpp:3-148): node i keeps the index of BVH2 node i and first holds the
+// boxes of that node's two children; then, top-down, a node repeatedly ADOPTS the children of its internal child with the largest
+// surface area as long as the result still fits in four slots.  Node 1 (the BVH2 alignment dummy) becomes the entry: its slot 0 points
+// at node 0, and traversal starts at (node 1, slot 0) -- for a BLAS at offset `root` in the shared array, at (root + 1, slot 0).
+struct QuadConverter {
+    const BVH2& in; BVH4& out;
+
+    void set_slot(Node4& n, int slot, const Box& b, int index, int count) {
+        n.lo_x[slot] = b.lo.x; n.lo_y[slot] = b.lo.y; n.lo_z[slot] = b.lo.z;
+        n.hi_x[slot] = b.hi.x; n.hi_y[slot] = b.hi.y; n.hi_z[slot] = b.hi.z;
+        n.child[slot].index = index; n.child[slot].count = count;
+    }
+    void copy_slot(Node4& dst, int d, const Node4& src, int s) {
+        dst.lo_x[d] = src.lo_x[s]; dst.lo_y[d] = src.lo_y[s]; dst.lo_z[d] = src.lo_z[s];
+        dst.hi_x[d] = src.hi_x[s]; dst.hi_y[d] = src.hi_y[s]; dst.hi_z[d] = src.hi_z[s];
+        dst.child[d] = src.child[s];
+    }
+    void adopt(int ni) {
+        Node4& n = out.nodes[size_t(ni)];
+        while (true) {
+            const int have = n.used();
+            int best = -1; float best_area = -std::numeric_limits<float>::infinity();
+            for (int i = 0; i < have; i++) {
+                if (n.child[i].count != 0) continue;                                    // leaves cannot be opened
+                const int theirs = out.nodes[size_t(n.child[i].index)].used();
+                if (have + theirs - 1 > 4) continue;
+                float dx = n.hi_x[i] - n.lo_x[i], dy = n.hi_y[i] - n.lo_y[i], dz = n.hi_z[i] - n.lo_z[i];
+                float half_area = dx * dy + dy * dz + dz * dx;
+                if (half_area > best_area) { best_area = half_area; best = i; }
+            }
+            if (best < 0) break;
+            const Node4 victim = out.nodes[size_t(n.child[best].index)];              // copy: its slots move up into this node
+            const int theirs = victim.used();
+            copy_slot(n, best, victim, 0);
+            for (int i = 1; i < theirs; i++) copy_slot(n, have + i - 1, victim, i);
+        }
+    }
+    void run() {
+        Node4 blank; std::memset(&blank, 0, sizeof(blank));
+        for (int i = 0; i < 4; i++) blank.child[i].index = blank.child[i].count = -1;
+        out.nodes.assign(in.nodes.size() < 2 ? 2 : in.nodes.size(), blank);
+        out.indices = in.indices;
+        for (size_t i = 0; i < in.nodes.size(); i++) {
+            if (i == 1 || in.nodes[i].leaf()) continue;
+            const int l = in.nodes[i].left_or_first;
+            for (int c = 0; c < 2; c++) {
+                const Node2& k = in.nodes[size_t(l + c)];
+                if (k.leaf()) set_slot(out.nodes[i], c, k.box, k.left_or_first, int(k.count()));
+                else          set_slot(out.nodes[i], c, k.box, l + c, 0);
+            }
+        }
+        out.nodes[1].child[0].index = 0; out.nodes[1].child[0].count = 0;              // entry slot
+        if (in.nodes[0].leaf()) { set_slot(out.nodes[0], 0, in.nodes[0].box, in.nodes[0].left_or_first, int(in.nodes[0].count())); return; }
+        std::vector<int> todo{ 0 };
+        while (!todo.empty()) {                                                         // top-down: a node is final before its children are opened
+            int ni = todo.back(); todo.pop_back();
+            adopt(ni);
+            const Node4& n = out.nodes[size_t(ni)];
+            for (int i = 0; i < n.used(); i++) if (n.child[i].count == 0) todo.push_back(n.child[i].index);
+        }
+    }
+};
+
 // ---------------------------------------------------------------- BVH2 leaf collapse
 struct Collapser {
     const BVH2& in; BVH2& out; float c_node, c_leaf;
@@ -686,8 +760,9 @@ struct SpatialBuilder {
 
 struct Built {
     BVH2 bvh2;
+    BVH4 bvh4;
     BVH8 bvh8;
-    int  kind; // 2 or 8
+    int  kind; // 2, 4 or 8
 };
 
 void prims_from_triangles(const float* pos, int n, Prims& p) {
@@ -713,6 +788,7 @@ Built* finish(Prims& prims, int kind, float sah_node, float sah_leaf) {
     } else {
         b->bvh2 = std::move(raw);
     }
+    if (kind == 4) QuadConverter{ b->bvh2, b->bvh4 }.run();          // 4-wide tree over the (leaf-collapsed) binary one
     return b;
 }
 
@@ -723,7 +799,7 @@ extern "C" {
 // Build over triangles: pos = n * 9 floats (v0,v1,v2). kind = 8 (CWBVH) or 2 (binary, SAH-collapsed leaves
 // when sah_leaf > 0; raw one-primitive leaves when sah_leaf <= 0).
 void* ptbh_build_triangles(const float* pos, int n, int kind, float sah_node, float sah_leaf) {
-    if (n <= 0 || (kind != 2 && kind != 8)) return nullptr;
+    if (n <= 0 || (kind != 2 && kind != 4 && kind != 8)) return nullptr;
     Prims p; prims_from_triangles(pos, n, p);
     return finish(p, kind, sah_node, sah_leaf);
 }
@@ -731,7 +807,7 @@ void* ptbh_build_triangles(const float* pos, int n, int kind, float sah_node, fl
 // Build over already-boxed primitives (TLAS over instance boxes): aabb = n * 6 floats (min,max); centers = box centers.
 // TLAS BVH2 is never leaf-collapsed (reference: BVH2Converter is a plain copy, BVHConverter.h:17-26).
 void* ptbh_build_boxes(const float* aabb, int n, int kind) {
-    if (n <= 0 || (kind != 2 && kind != 8)) return nullptr;
+    if (n <= 0 || (kind != 2 && kind != 4 && kind != 8)) return nullptr;
     Prims p; p.box.resize(n); p.center.resize(n);
     for (int i = 0; i < n; i++) {
         const float* a = aabb + size_t(i) * 6;
@@ -746,7 +822,7 @@ void* ptbh_build_boxes(const float* aabb, int n, int kind) {
 // the kind the kernels walk, without rebuilding: kind 8 -> CWBVH, kind 2 -> SAH leaf collapse (sah_leaf > 0) or a plain copy.
 // nodes: n_nodes x 32 bytes (BVH.h:11-23 layout, node 1 = dummy); returns null on a malformed tree.
 void* ptbh_from_bvh2(const void* nodes, int n_nodes, const int* indices, int n_indices, int kind, float sah_node, float sah_leaf) {
-    if (!nodes || !indices || n_nodes < 1 || n_indices < 1 || (kind != 2 && kind != 8)) return nullptr;
+    if (!nodes || !indices || n_nodes < 1 || n_indices < 1 || (kind != 2 && kind != 4 && kind != 8)) return nullptr;
     BVH2 raw;
     raw.nodes.resize(size_t(n_nodes)); std::memcpy(raw.nodes.data(), nodes, size_t(n_nodes) * sizeof(Node2));
     raw.indices.assign(indices, indices + n_indices);
@@ -769,6 +845,7 @@ void* ptbh_from_bvh2(const void* nodes, int n_nodes, const int* indices, int n_i
     if (kind == 8) WideConverter(raw, b->bvh8).run();
     else if (sah_leaf > 0.0f) { Collapser c{ raw, b->bvh2, sah_node, sah_leaf, {} }; c.run(); }
     else b->bvh2 = std::move(raw);
+    if (kind == 4) QuadConverter{ b->bvh2, b->bvh4 }.run();
     return b;
 }
 
@@ -875,9 +952,9 @@ void ptbh_trace_stats(void* h, const float* pos, const float* rays, int n_rays, 
 }
 
 int ptbh_kind(void* h)        { return static_cast<Built*>(h)->kind; }
-int ptbh_node_count(void* h)  { Built* b = static_cast<Built*>(h); return int(b->kind == 8 ? b->bvh8.nodes.size() : b->bvh2.nodes.size()); }
+int ptbh_node_count(void* h)  { Built* b = static_cast<Built*>(h); return int(b->kind == 8 ? b->bvh8.nodes.size() : b->kind == 4 ? b->bvh4.nodes.size() : b->bvh2.nodes.size()); }
 int ptbh_index_count(void* h) { Built* b = static_cast<Built*>(h); return int(b->kind == 8 ? b->bvh8.indices.size() : b->bvh2.indices.size()); }
-int ptbh_node_bytes(void* h)  { return static_cast<Built*>(h)->kind == 8 ? 80 : 32; }
+int ptbh_node_bytes(void* h)  { int k = static_cast<Built*>(h)->kind; return k == 8 ? 80 : k == 4 ? 128 : 32; }
 
 // Copies nodes (80 or 32 bytes each) and primitive order out; adds the given offsets so the caller can
 // concatenate many BLAS into one node/triangle array (reference: Integrator.cpp:252-277 / 184-207).
@@ -891,6 +968,17 @@ void ptbh_export(void* h, void* nodes_out, int* indices_out, int node_offset, in
             dst[i].base_triangle += uint32_t(index_offset);
         }
         std::memcpy(indices_out, b->bvh8.indices.data(), b->bvh8.indices.size() * sizeof(int));
+    } else if (b->kind == 4) {
+        // Integrator.cpp:216-246: leaf slots move by the primitive offset, internal slots (and the entry slot of node 1) by the node offset
+        Node4* dst = static_cast<Node4*>(nodes_out);
+        for (size_t i = 0; i < b->bvh4.nodes.size(); i++) {
+            dst[i] = b->bvh4.nodes[i];
+            for (int c = 0; c < 4; c++) {
+                if (dst[i].child[c].count == -1) break;
+                dst[i].child[c].index += dst[i].child[c].count > 0 ? index_offset : node_offset;
+            }
+        }
+        std::memcpy(indices_out, b->bvh4.indices.data(), b->bvh4.indices.size() * sizeof(int));
     } else {
         Node2* dst = static_cast<Node2*>(nodes_out);
         for (size_t i = 0; i < b->bvh2.nodes.size(); i++) {

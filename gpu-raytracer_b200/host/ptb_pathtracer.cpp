@@ -7,7 +7,7 @@
 namespace ptb {
 
 Pathtracer::Pathtracer(const ptb_scene& scene, const CameraDesc& cam, int device, int rank, int world, int band_rows)
-    : camera(cam), scene_(scene), device_(device), rank_(rank), world_(world), band_rows_(band_rows) {
+    : camera(cam), scene_(scene), device_(device), rank_(rank), world_(world), band_rows_(band_rows), mesh_count_(scene.mesh_count) {
     // defaults of GPUConfig (Common.h:39-67)
     std::memset(&gpu_config, 0, sizeof(gpu_config));
     gpu_config.reconstruction_filter = 2; gpu_config.aov_mask = 1u; gpu_config.num_bounces = 10;
@@ -17,7 +17,7 @@ Pathtracer::Pathtracer(const ptb_scene& scene, const CameraDesc& cam, int device
     gpu_config.sigma_z = 4.0f; gpu_config.sigma_n = 16.0f; gpu_config.sigma_l = 10.0f;
 }
 
-Pathtracer::~Pathtracer() { cuda_free(); }
+Pathtracer::~Pathtracer() { cuda_free(); delete[] moved_xf_; }
 
 void Pathtracer::check(int code, const char* what) {
     if (code != 0) throw Error(std::string(what) + " failed: " + ptb_error_string(code), code);
@@ -107,7 +107,14 @@ void Pathtracer::update(float) {
         pixel_query.pixel_index = -1;
         pixel_query_status = PixelQueryStatus::OUTPUT_READY;
     }
-    const bool camera_moved = invalidated_camera;
+    bool scene_moved = false;
+    if (invalidated_scene && moved_xf_) {                              // Integrator.cpp:441-452: build_tlas() -- here a refit on the device
+        check(ptb_refit_instances(ctx_, moved_xf_, moved_xf_ + size_t(mesh_count_) * 12, nullptr), "ptb_refit_instances");
+        delete[] moved_xf_; moved_xf_ = nullptr;
+        scene_moved = true;
+    }
+    invalidated_scene = false;
+    const bool camera_moved = invalidated_camera || scene_moved;
     if (invalidated_camera) {
         upload_camera();
         invalidated_camera = false;
@@ -124,6 +131,15 @@ void Pathtracer::update(float) {
     } else {
         sample_index++;                                                // Integrator.cpp:518-526
     }
+}
+
+void Pathtracer::move_instances(const float* transforms, const float* transforms_inv) {
+    if (!transforms || !transforms_inv || mesh_count_ <= 0) throw Error("move_instances without a scene", PTB_E_BADARG);
+    const size_t n = size_t(mesh_count_) * 12;
+    if (!moved_xf_) moved_xf_ = new float[2 * n];
+    std::memcpy(moved_xf_, transforms, n * sizeof(float));
+    std::memcpy(moved_xf_ + n, transforms_inv, n * sizeof(float));
+    invalidated_scene = true;
 }
 
 void Pathtracer::render() {

@@ -61,6 +61,10 @@ public:
     void update(float delta) override;                                                              // Integrator.cpp:432-528
     void render() override;                                                                         // Pathtracer.cpp:738-855
     void set_pixel_query(int x, int y);                                                             // Integrator.h:266-277
+    // Moving instances (the role of Mesh::update + invalidated_scene + build_tlas, Integrator.cpp:399-430,441-452): new object-to-world
+    // and world-to-object matrices, mesh_count x 12 floats each in table order; the next update() refits the TLAS on the device
+    // (ptb_refit_instances) and restarts the accumulation.
+    void move_instances(const float* transforms, const float* transforms_inv);
 
     void aov_enable(AOVType t)  { gpu_config.aov_mask |=  (1u << int(t)); invalidated_aovs = true; invalidated_gpu_config = true; }
     void aov_disable(AOVType t) { gpu_config.aov_mask &= ~(1u << int(t)); invalidated_aovs = true; invalidated_gpu_config = true; }
@@ -87,6 +91,8 @@ private:
     bool have_block_ = false;
     ptb_camera block_;
     float block_vp_[16];
+    float* moved_xf_ = nullptr;           // pending transforms of move_instances (2 x mesh_count x 12 floats), owned
+    int mesh_count_ = 0;
 };
 
 }  // namespace ptb

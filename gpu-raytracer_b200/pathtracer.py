@@ -148,7 +148,7 @@ def fill_scene_struct(blob, keep):
         keep.append(a)
         return a.ctypes.data
     s = PtbScene()
-    node_bytes = 80 if int(blob["bvh_kind"]) == 8 else 32
+    node_bytes = {8: 80, 4: 128, 2: 32}[int(blob["bvh_kind"])]
     s.triangles = arr("triangles"); s.triangle_count = int(blob["triangles"].shape[0])
     s.bvh_nodes = arr("bvh_nodes"); s.bvh_node_count = int(blob["bvh_nodes"].size // node_bytes)
     s.bvh_kind = int(blob["bvh_kind"]); s.tlas_node_count = int(blob["tlas_node_count"])

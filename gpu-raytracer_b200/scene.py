@@ -757,7 +757,7 @@ def build_blob(desc: SceneDesc, bvh_kind=8, width=None, height=None, threads=Non
                              zip(desc.mesh_datas, files)))
     t_blas = time.perf_counter() - t0
 
-    node_bytes = 80 if bvh_kind == 8 else 32
+    node_bytes = {8: 80, 4: 128, 2: 32}[int(bvh_kind)]
     node_off, tri_off = [], []
     n_nodes, n_tris = 2 * M, 0
     for b in blas:

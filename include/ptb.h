@@ -77,7 +77,7 @@ typedef struct ptb_scene {
     int32_t        triangle_count;
     const void*    bvh_nodes;            /* node_count x 80 B (CWBVH) or 32 B (binary); TLAS in [0, 2*mesh_count) */
     int32_t        bvh_node_count;
-    int32_t        bvh_kind;             /* 8 or 2 */
+    int32_t        bvh_kind;             /* 8 (CWBVH, 80-byte nodes), 4 (BVH4, 128-byte nodes; BLAS entry = root + 1) or 2 (32-byte nodes) */
     int32_t        tlas_node_count;
     int32_t        mesh_count;           /* instances, in TLAS leaf order */
     const int32_t* mesh_bvh_root_indices;/* root | identity << 31 */

@@ -112,6 +112,13 @@ static int size_trace_kernel(Kernel& k, int elem) {   // Integrator.h:280-295
     k.smem = (unsigned)(elem == 8 ? smem_for_block_8(block) : smem_for_block_4(block));
     return 0;
 }
+static const char* trace_kernel_name(int kind, bool shadow) {          // Pathtracer.cpp:93-107: one pair of trace kernels per BVH type
+    if (kind == 8) return shadow ? "kernel_trace_shadow_bvh8" : "kernel_trace_bvh8";
+    if (kind == 4) return shadow ? "kernel_trace_shadow_bvh4" : "kernel_trace_bvh4";
+    return shadow ? "kernel_trace_shadow_bvh2" : "kernel_trace_bvh2";
+}
+static const char* node_global_name(int kind) { return kind == 8 ? "bvh8_nodes" : kind == 4 ? "bvh4_nodes" : "bvh2_nodes"; }
+static size_t node_size(int kind) { return kind == 8 ? 80 : kind == 4 ? 128 : 32; }
 static int size_2d_kernel(ref_ctx* c, Kernel& k) {    // CUDAKernel.h:67-81, Pathtracer.cpp:276-282
     int grid = 0, block = 0;
     RCK(cuOccupancyMaxPotentialBlockSize(&grid, &block, k.fn, nullptr, 0, 0));
@@ -297,8 +304,8 @@ int ref_upload_scene(ref_ctx* c, const ptb_scene* s) {
     e |= set_global(c, "screen_width", c->width); e |= set_global(c, "screen_pitch", c->pitch); e |= set_global(c, "screen_height", c->height);
     if (e) return e;
     // kernels + launch dims (Pathtracer.cpp:76-145)
-    const char* tname = s->bvh_kind == 8 ? "kernel_trace_bvh8" : "kernel_trace_bvh2";
-    const char* sname = s->bvh_kind == 8 ? "kernel_trace_shadow_bvh8" : "kernel_trace_shadow_bvh2";
+    const char* tname = trace_kernel_name(s->bvh_kind, false);
+    const char* sname = trace_kernel_name(s->bvh_kind, true);
     e |= get_kernel(c, c->generate, "kernel_generate"); e |= get_kernel(c, c->trace, tname); e |= get_kernel(c, c->trace_shadow, sname);
     e |= get_kernel(c, c->sort, "kernel_sort"); e |= get_kernel(c, c->accumulate, "kernel_accumulate");
     e |= get_kernel(c, c->material[0], "kernel_material_diffuse"); e |= get_kernel(c, c->material[1], "kernel_material_plastic");
@@ -317,8 +324,8 @@ int ref_upload_scene(ref_ctx* c, const ptb_scene* s) {
     // geometry
     CUdeviceptr p;
     e = dupload(c, &p, s->triangles, (size_t)s->triangle_count * 96); if (e) return e; e = set_global(c, "triangles", p); if (e) return e;
-    e = dupload(c, &p, s->bvh_nodes, (size_t)s->bvh_node_count * (s->bvh_kind == 8 ? 80 : 32)); if (e) return e;
-    e = set_global(c, s->bvh_kind == 8 ? "bvh8_nodes" : "bvh2_nodes", p); if (e) return e;
+    e = dupload(c, &p, s->bvh_nodes, (size_t)s->bvh_node_count * node_size(s->bvh_kind)); if (e) return e;
+    e = set_global(c, node_global_name(s->bvh_kind), p); if (e) return e;
     e = dupload(c, &p, s->mesh_bvh_root_indices, (size_t)s->mesh_count * 4); if (e) return e; e = set_global(c, "mesh_bvh_root_indices", p); if (e) return e;
     e = dupload(c, &p, s->mesh_material_ids, (size_t)s->mesh_count * 4); if (e) return e; e = set_global(c, "mesh_material_ids", p); if (e) return e;
     e = dupload(c, &p, s->mesh_transforms, (size_t)s->mesh_count * 48); if (e) return e; e = set_global(c, "mesh_transforms", p); if (e) return e;
@@ -623,8 +630,8 @@ int ref_ao_upload_scene(ref_ctx* c, const ptb_scene* s) {
     e |= set_global(c, "screen_width", c->width); e |= set_global(c, "screen_pitch", c->pitch); e |= set_global(c, "screen_height", c->height);
     if (e) return e;
     e |= get_kernel(c, c->generate, "kernel_generate");
-    e |= get_kernel(c, c->trace, s->bvh_kind == 8 ? "kernel_trace_bvh8" : "kernel_trace_bvh2");
-    e |= get_kernel(c, c->trace_shadow, s->bvh_kind == 8 ? "kernel_trace_shadow_bvh8" : "kernel_trace_shadow_bvh2");
+    e |= get_kernel(c, c->trace, trace_kernel_name(s->bvh_kind, false));
+    e |= get_kernel(c, c->trace_shadow, trace_kernel_name(s->bvh_kind, true));
     e |= get_kernel(c, c->sort, "kernel_ambient_occlusion"); e |= get_kernel(c, c->accumulate, "kernel_accumulate");
     if (e) return e;
     size_1d_kernel(c->generate); size_1d_kernel(c->sort);
@@ -633,8 +640,8 @@ int ref_ao_upload_scene(ref_ctx* c, const ptb_scene* s) {
     if (e) return e;
     CUdeviceptr p;
     e = dupload(c, &p, s->triangles, (size_t)s->triangle_count * 96); if (e) return e; e = set_global(c, "triangles", p); if (e) return e;
-    e = dupload(c, &p, s->bvh_nodes, (size_t)s->bvh_node_count * (s->bvh_kind == 8 ? 80 : 32)); if (e) return e;
-    e = set_global(c, s->bvh_kind == 8 ? "bvh8_nodes" : "bvh2_nodes", p); if (e) return e;
+    e = dupload(c, &p, s->bvh_nodes, (size_t)s->bvh_node_count * node_size(s->bvh_kind)); if (e) return e;
+    e = set_global(c, node_global_name(s->bvh_kind), p); if (e) return e;
     e = dupload(c, &p, s->mesh_bvh_root_indices, (size_t)s->mesh_count * 4); if (e) return e; e = set_global(c, "mesh_bvh_root_indices", p); if (e) return e;
     e = dupload(c, &p, s->mesh_material_ids, (size_t)s->mesh_count * 4); if (e) return e; e = set_global(c, "mesh_material_ids", p); if (e) return e;
     e = dupload(c, &p, s->mesh_transforms, (size_t)s->mesh_count * 48); if (e) return e; e = set_global(c, "mesh_transforms", p); if (e) return e;

@@ -249,3 +249,52 @@ def test_sbvh_children_stay_inside_their_parents():
     _, _, t, hit_tri = scene.trace_stats(sb, tri, rays)
     _, _, t_ref, _ = scene.trace_stats(scene.build_blas(tri, 8), tri, rays)
     assert np.array_equal(t.view(np.uint32), t_ref.view(np.uint32)) and np.isfinite(t).mean() > 0.9     # a ray through each centroid
+
+
+def test_bvh4_conversion_is_a_valid_tree():
+    """QuadConverter (Src/BVH/Converters/BVH4Converter.cpp): starting at (node 1, slot 0) every primitive is reached exactly once, every
+    slot box contains what hangs below it, unused slots trail, and children were adopted (more than two used slots per node on average)."""
+    rng = np.random.default_rng(11)
+    n = 3000
+    c = rng.uniform(-5, 5, (n, 1, 3)).astype(np.float32)
+    tri = (c + rng.normal(0, 0.15, (n, 3, 3))).astype(np.float32)
+    for leaf_cost in (1.0, 0.0):
+        b = scene.build_blas(tri, 4, 4.0, leaf_cost)
+        assert b.kind == 4 and b.node_bytes == 128
+        raw, idx = b.export(0, 0)
+        nodes = raw.view(np.float32).reshape(-1, 32)
+        ic = raw.view(np.int32).reshape(-1, 32)[:, 24:].reshape(-1, 4, 2)
+        assert np.array_equal(np.sort(idx), np.arange(n))
+        assert ic[1, 0, 0] == 0 and ic[1, 0, 1] == 0                  # the entry slot points at node 0
+        seen = np.zeros(n, dtype=np.int32); used = []
+
+        def walk(node, slot):
+            index, count = int(ic[node, slot, 0]), int(ic[node, slot, 1])
+            lo = np.array([np.inf] * 3); hi = -lo
+            if count > 0:
+                for t in range(index, index + count):
+                    seen[idx[t]] += 1
+                    lo = np.minimum(lo, tri[idx[t]].min(0)); hi = np.maximum(hi, tri[idx[t]].max(0))
+            else:
+                k = 0
+                while k < 4 and ic[index, k, 1] != -1:
+                    k += 1
+                assert k >= 1 and all(ic[index, j, 1] == -1 for j in range(k, 4))
+                used.append(k)
+                for j in range(k):
+                    clo, chi = walk(index, j)
+                    box_lo = nodes[index, [j, 4 + j, 8 + j]]; box_hi = nodes[index, [12 + j, 16 + j, 20 + j]]
+                    assert np.all(box_lo <= clo + 1e-6) and np.all(box_hi >= chi - 1e-6)
+                    lo = np.minimum(lo, clo); hi = np.maximum(hi, chi)
+            return lo, hi
+
+        import sys
+        sys.setrecursionlimit(10000)
+        walk(1, 0)
+        assert np.all(seen == 1)
+        assert np.mean(used) > 2.5
+    # offsets as the aggregated arrays need them (Integrator.cpp:216-246)
+    raw2, _ = b.export(100, 5000)
+    ic2 = raw2.view(np.int32).reshape(-1, 32)[:, 24:].reshape(-1, 4, 2)
+    inner = ic[:, :, 1] == 0; leaf = ic[:, :, 1] > 0
+    assert np.array_equal(ic2[:, :, 0][inner], ic[:, :, 0][inner] + 100) and np.array_equal(ic2[:, :, 0][leaf], ic[:, :, 0][leaf] + 5000)

@@ -92,6 +92,45 @@ def test_reference_kernels_bit_exact(cases, name):
         p.close(); r.close()
 
 
+@pytest.mark.parametrize("kind_name,size", [("soup", (256, 160)), ("cornell", (192, 192)), ("atrium", (320, 192))])
+def test_bvh4_against_reference_kernels(kind_name, size):
+    """The 4-wide BVH (`--bvh bvh4`, Src/CUDA/Raytracing/BVH4.h, Src/BVH/Converters/BVH4Converter.cpp): host/bvh_build.cpp's QuadConverter
+    builds the 128-byte nodes, k_trace4 walks them; the reference's kernel_trace_bvh4 / kernel_trace_shadow_bvh4 get the same node array.
+    Instanced scenes (transformed BLAS entries included): hits, all six AOVs, display and ray counters bit for bit."""
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref
+    d = scene.procedural_scene(kind_name, seed=7, width=size[0], height=size[1], detail=0.5)
+    blob = scene.build_blob(d, 4, rng="fallback")
+    assert int(blob["bvh_kind"]) == 4 and np.asarray(blob["bvh_nodes"]).size % 128 == 0
+    w = size[0]
+    for nb in (1, 3):
+        cfg = pt.default_config(num_bounces=nb, aov_mask=0x3F)
+        p = pt.Pathtracer(blob, config=cfg); r = ref.Reference(blob, config=cfg)
+        p.render_frames(2); r.render_frames(2)
+        if nb == 1:
+            assert valid_hits_equal(p.primary_hits()[:, :w], r.primary_hits()[:, :w]).all()
+        for k in range(6):
+            a, b = p.get_aov(k)[:, :w], r.get_aov(k)[:, :w]
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (nb, pt.AOV_NAMES[k])
+        assert np.array_equal(p.get_display()[:, :w].view(np.uint32), r.get_display()[:, :w].view(np.uint32))
+        sp, sr = p.ray_stats(), r.ray_stats()
+        assert np.array_equal(sp["trace"], sr["trace"]) and np.array_equal(sp["shadow"], sr["shadow"]) and np.array_equal(sp["shaded"], sr["shaded"])
+        if nb == 3:
+            trav = p.measure_traversal(1)
+            assert trav["nodes"][0] > 0 and trav["triangles"][0] > 0
+        p.close(); r.close()
+    # the same picture as the CWBVH path on the same scene (any valid BVH, same closest hits)
+    blob8 = scene.build_blob(d, 8, rng="fallback")
+    cfg = pt.default_config(num_bounces=1, aov_mask=0x39)
+    p4 = pt.Pathtracer(blob, config=cfg); p8 = pt.Pathtracer(blob8, config=cfg); p8.set_static_merge(0)
+    p4.render_frames(1); p8.render_frames(1)
+    for k in (pt.AOV_ALBEDO, pt.AOV_NORMAL, pt.AOV_POSITION):
+        a, b = p4.get_aov(k)[:, :w], p8.get_aov(k)[:, :w]
+        assert np.mean(np.any(a.view(np.uint32) != b.view(np.uint32), axis=-1)) <= 0.002, pt.AOV_NAMES[k]
+    p4.close(); p8.close()
+
+
 @pytest.mark.parametrize("flags", [dict(enable_next_event_estimation=0), dict(enable_multiple_importance_sampling=0), dict(enable_russian_roulette=0),
                                    dict(reconstruction_filter=0), dict(reconstruction_filter=1), dict(enable_mipmapping=0)])
 def test_config_switches_bit_exact(cases, flags):
