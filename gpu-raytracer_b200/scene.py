@@ -1111,11 +1111,24 @@ class _MitsubaWalker:
 
     def shape_mesh(self, node):
         typ = node.get("type")
-        if typ == "obj":
+        if typ in ("obj", "ply", "serialized", "hair"):                    # MitsubaLoader.cpp:434-515
+            from . import mesh_loaders
             path = os.path.join(self.base, _child_by_name(node, "filename").get("value").replace("\\", "/"))
-            if path not in self.mesh_cache:
-                self.mesh_cache[path] = self.desc.add_mesh_data(load_obj(path), source=path)
-            return self.mesh_cache[path]
+            key, source = path, path
+            if typ == "serialized":
+                shape_index = int(_child_value(node, "shapeIndex", 0))
+                key, source = "%s#%d" % (path, shape_index), "%s.shape_%d" % (path, shape_index)      # the .bvh cache is per sub-mesh (:495)
+            if key not in self.mesh_cache:
+                if typ == "obj":
+                    tri = load_obj(path)
+                elif typ == "ply":
+                    tri = mesh_loaders.load_ply(path)
+                elif typ == "serialized":
+                    tri = mesh_loaders.load_serialized(path, shape_index)
+                else:
+                    tri = mesh_loaders.load_hair(path, float(_child_value(node, "radius", 0.0025)))
+                self.mesh_cache[key] = self.desc.add_mesh_data(tri, source=source if typ == "obj" else None)
+            return self.mesh_cache[key]
         m = _parse_transform_matrix(node)
         if typ == "rectangle":
             return self.desc.add_mesh_data(geo_rectangle(m))
