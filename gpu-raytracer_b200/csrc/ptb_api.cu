@@ -165,6 +165,16 @@ struct ptb_ctx {
 extern "C" {
 void* ptbh_build_triangles(const float* pos, int n, int kind, float sah_node, float sah_leaf);
 void* ptbh_build_triangles_sbvh(const float* pos, int n, float alpha, int bins, float max_dup);
+void  ptbh_set_tri_cost(float c);
+#ifndef PTB_MERGE_ALPHA_DEFAULT
+#define PTB_MERGE_ALPHA_DEFAULT 3e-4f
+#endif
+#ifndef PTB_MERGE_BINS_DEFAULT
+#define PTB_MERGE_BINS_DEFAULT 96
+#endif
+#ifndef PTB_MERGE_TRICOST_DEFAULT
+#define PTB_MERGE_TRICOST_DEFAULT 1.0f
+#endif
 int   ptbh_node_count(void* h);
 int   ptbh_index_count(void* h);
 void  ptbh_export(void* h, void* nodes_out, int* indices_out, int node_offset, int index_offset);
@@ -724,7 +734,15 @@ static int rebuild_static_merge(ptb_ctx* ctx) {
     std::vector<unsigned char> dfs;
     std::vector<int> order;
     for (int attempt = ctx->merge_spatial ? 0 : 1; attempt < 2; attempt++) {
-        h = attempt == 0 ? ptbh_build_triangles_sbvh(pos.data(), n, 3e-4f, 96, 2.0f) : ptbh_build_triangles(pos.data(), n, 8, 4.0f, 1.0f);
+        // builder parameters: A/B overrides for tools/ (PTB_MERGE_ALPHA / _BINS / _DUP / _TRICOST); the defaults are the measured best
+        float alpha = PTB_MERGE_ALPHA_DEFAULT, dup = 2.0f, tri_cost = PTB_MERGE_TRICOST_DEFAULT; int bins = PTB_MERGE_BINS_DEFAULT;
+        if (const char* v = getenv("PTB_MERGE_ALPHA")) alpha = (float)atof(v);
+        if (const char* v = getenv("PTB_MERGE_BINS")) bins = atoi(v);
+        if (const char* v = getenv("PTB_MERGE_DUP")) dup = (float)atof(v);
+        if (const char* v = getenv("PTB_MERGE_TRICOST")) tri_cost = (float)atof(v);
+        ptbh_set_tri_cost(tri_cost);
+        h = attempt == 0 ? ptbh_build_triangles_sbvh(pos.data(), n, alpha, bins, dup) : ptbh_build_triangles(pos.data(), n, 8, 4.0f, 1.0f);
+        ptbh_set_tri_cost(1.0f);
         if (!h) return PTB_E_STATE;
         nm = ptbh_node_count(h);
         dfs.assign((size_t)nm * 80, 0); order.assign((size_t)ptbh_index_count(h), 0);

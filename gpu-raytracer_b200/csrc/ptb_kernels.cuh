@@ -675,6 +675,10 @@ PTB_DI void deposit(const Frame& P, int bounce, int px, float3 at_bounce0, float
 #ifndef PTB_SORT_MIN_BLOCKS
 #define PTB_SORT_MIN_BLOCKS 4
 #endif
+#ifndef PTB_SORT_PREFETCH
+#define PTB_SORT_PREFETCH 1     // measured: k_sort 1.44 -> 1.33 ms per frame (profiles/r2_summary.md)
+#endif
+PTB_DI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 // one atomic per group of lanes that are active at the call site (divergent code: the rare medium-scatter emission of k_sort)
 PTB_DI int append_active(int* counter) {
     unsigned act = __activemask();
@@ -691,6 +695,16 @@ __global__ void __launch_bounds__(256, PTB_SORT_MIN_BLOCKS) k_sort(const __grid_
     const int rounded = (count + 31) & ~31;     // whole warps iterate together so the aggregated appends stay converged
     for (int index = blockIdx.x * blockDim.x + threadIdx.x; index < rounded; index += gridDim.x * blockDim.x) {
         int dest = -1;                            // material queue to join: 0..3, -1 = path ended (or scattered)
+#if PTB_SORT_PREFETCH
+        {   // the kernel waits on HBM (ncu: long_scoreboard): pull the next grid-stride iteration's records into L2 while this one is processed
+            const int nxt = index + PTB_SORT_PREFETCH * int(gridDim.x * blockDim.x);
+            if (nxt < count) {
+                prefetch_l2(q.od0 + nxt); prefetch_l2(q.od1 + nxt); prefetch_l2(q.hit + nxt);
+                if (bounce > 0) prefetch_l2(q.path + nxt);
+                if ((threadIdx.x & 7u) == 0) prefetch_l2(q.pix + nxt);
+            }
+        }
+#endif
         if (index < count) {
             float4 a = q.od0[index], b = q.od1[index];
             float3 ray_direction = f3(a.w, b.x, b.y);
@@ -1090,6 +1104,9 @@ PTB_DI float2 ellipse_axis_to_gradient(const TriFull& t, float inv_2area, float3
 // ------------------------------------------------------------------------------------------ shade + NEE + extend
 // Src/CUDA/Pathtracer.cu:465-757.  One kernel instantiation per BSDF; shadow rays and extension rays are appended
 // with warp-aggregated atomics.
+#ifndef PTB_SHADE_PREFETCH
+#define PTB_SHADE_PREFETCH 0
+#endif
 template <typename BSDF> struct ShadeOccupancy { static constexpr int min_blocks = 2; };        // microfacet BSDFs: ~120 registers
 template <> struct ShadeOccupancy<BSDFDiffuse> { static constexpr int min_blocks = PTB_SHADE_MIN_BLOCKS_DIFFUSE; };
 template <typename BSDF>
@@ -1102,6 +1119,11 @@ __global__ void __launch_bounds__(256, ShadeOccupancy<BSDF>::min_blocks) k_shade
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
         bool emit_shadow = false, emit_next = false;
         float4 sh0, sh1, sh_ill, nx0, nx1, nx_path; unsigned nx_pix = 0; int nx_medium = PTB_INVALID;
+#if PTB_SHADE_PREFETCH
+        const int i_next = i + int(gridDim.x * blockDim.x);
+        int index_next = -1;
+        if (i_next < count) index_next = __ldg(queue + i_next);     // issued now, consumed after this iteration's own loads are in flight
+#endif
         if (i < count) {
             const int index = queue[i];
             float4 a = q.od0[index], b = q.od1[index];
@@ -1119,6 +1141,13 @@ __global__ void __launch_bounds__(256, ShadeOccupancy<BSDF>::min_blocks) k_shade
             if (bounce > 0) { float4 p = q.path[index]; throughput = f3(p.x, p.y, p.z); }
 
             TriFull tri = load_tri_full(P, hit.triangle_id);
+#if PTB_SHADE_PREFETCH
+            if (index_next >= 0) {       // next iteration's gathered records -> L2 while this one computes
+                prefetch_l2(q.od0 + index_next); prefetch_l2(q.od1 + index_next); prefetch_l2(q.hit + index_next);
+                prefetch_l2(q.pix + index_next);
+                if (bounce > 0) prefetch_l2(q.path + index_next);
+            }
+#endif
             float3 hit_point = barycentric(hit.u, hit.v, tri.p0, tri.e1, tri.e2);
             float3 normal = barycentric(hit.u, hit.v, tri.n0, tri.ne1, tri.ne2);
             float2 tex_coord = barycentric(hit.u, hit.v, tri.t0, tri.te1, tri.te2);
@@ -1318,6 +1347,9 @@ __global__ void __launch_bounds__(256) k_ambient_occlusion(const __grid_constant
 // ------------------------------------------------------------------------------------------ accumulate (+ clear)
 // kernel_accumulate (Pathtracer.cu:775-796, AOV.h:35-46) fused with the framebuffer clear the reference does with
 // separate memsets (Integrator.cpp:377-383): one read-modify-write pass over HBM per enabled AOV instead of two.
+#ifndef PTB_ACC_BATCH
+#define PTB_ACC_BATCH 9     // slot planes whose loads are in flight together (one batch for the bench's 9-pass wave: 0.39 -> 0.115 ms; 4: 0.39, 12: 0.23)
+#endif
 __global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ Frame P) {
     const bool push = P.xchg.count > 0 && P.xchg.push;
     size_t plane = 0;
@@ -1333,15 +1365,15 @@ __global__ void __launch_bounds__(256) k_accumulate(const __grid_constant__ Fram
             float4 acc = averaged ? P.aov[k].acc[px] : f4(0.0f);
             // fold the slot planes in pass order (same arithmetic as one kernel_accumulate per pass); the loads of four planes are
             // issued together -- a plain loop serialises nine dependent-looking HBM round trips per pixel (0.72 -> 0.2 ms per frame)
-            for (int s0 = 0; s0 < P.wave_samples; s0 += 4) {
-                float4 fb[4];
+            for (int s0 = 0; s0 < P.wave_samples; s0 += PTB_ACC_BATCH) {
+                float4 fb[PTB_ACC_BATCH];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
+                for (int j = 0; j < PTB_ACC_BATCH; j++) {
                     size_t fbi = size_t(s0 + j) * P.fb_stride + px;
                     fb[j] = (averaged && s0 + j < P.wave_samples) ? __ldcs(P.aov[k].fb + fbi) : f4(0.0f);
                 }
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
+                for (int j = 0; j < PTB_ACC_BATCH; j++) {
                     if (s0 + j >= P.wave_samples) break;
                     if (averaged) {
                         float n = float(P.first_sample + s0 + j);

@@ -25,8 +25,8 @@ ms = e0.elapsed_time(e1) / 10
 crc = zlib.crc32(p.get_aov(0).tobytes())
 p.set_timing(True); p.render_frame(8); p.sync(); st = p.stage_ms(); p.set_timing(False)
 tr = p.measure_traversal(1)
-print("RESULT mode=%%d %%.3f ms crc=%%08x trace=%%.2f shadow=%%.2f sort=%%.2f shade=%%.2f | closest nodes/ray %%.2f tris/ray %%.2f | shadow nodes/ray %%.2f tris/ray %%.2f" %% (
-    mode, ms, crc, st["trace"], st["shadow_trace"], st["sort"], st["shade"], tr["nodes"][0] / tr["rays"][0], tr["triangles"][0] / tr["rays"][0],
+print("RESULT mode=%%d %%.3f ms crc=%%08x trace=%%.2f shadow=%%.2f sort=%%.3f shade=%%.3f acc=%%.3f | closest nodes/ray %%.2f tris/ray %%.2f | shadow nodes/ray %%.2f tris/ray %%.2f" %% (
+    mode, ms, crc, st["trace"], st["shadow_trace"], st["sort"], st["shade"], st["accumulate_or_svgf"], tr["nodes"][0] / tr["rays"][0], tr["triangles"][0] / tr["rays"][0],
     tr["nodes"][1] / max(tr["rays"][1], 1), tr["triangles"][1] / max(tr["rays"][1], 1)))
 del s, e0, e1
 p.close()
