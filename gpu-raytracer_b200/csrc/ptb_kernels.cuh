@@ -16,7 +16,9 @@
 #endif
 #define PTB_STACK_TOTAL 32                // BVH_STACK_SIZE, Common.h:104
 #define PTB_LOCAL_STACK (PTB_STACK_TOTAL - PTB_SM_STACK)
-#define PTB_TLAS_STAGE_MAX_NODES 256      // up to 20 KB of TLAS nodes bulk-copied (TMA) into shared memory per CTA
+#ifndef PTB_TLAS_STAGE_MAX_NODES
+#define PTB_TLAS_STAGE_MAX_NODES 128      // up to 10 KB of nodes bulk-copied (TMA) into shared memory per CTA; 256 / 384 were slower (they shrink the L1:
+#endif                                    // profiles/r2_variants_smem_vs_l1.log), 8 .. 128 within noise of each other
 #ifndef PTB_DYNFETCH_ND
 #define PTB_DYNFETCH_ND 2                 // dynamic fetch heuristic, Ylitie et al. 2017 section 4.4 (BVH8.h:109-111 uses 4 / 16; 2 / 8 measured 1.6 % faster here)
 #endif
@@ -25,6 +27,9 @@
 #endif
 #ifndef PTB_POSTPONE_DIVISOR
 #define PTB_POSTPONE_DIVISOR 5            // triangle postponing threshold (BVH8.h:12-15)
+#endif
+#ifndef PTB_STAGE_MERGED_TOP
+#define PTB_STAGE_MERGED_TOP 1            // stage the merged tree's top levels whenever a merged tree exists (0: only when the TLAS is never walked)
 #endif
 #ifndef PTB_SHADE_MIN_BLOCKS_DIFFUSE
 #define PTB_SHADE_MIN_BLOCKS_DIFFUSE 4    // 64 registers (120 B of spills) but twice the gathers in flight: frame 32.72 -> 32.21 ms
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
     TraceShared S;
     // staged in shared memory: the TLAS, or -- when every instance is merged and the TLAS is never walked -- the top levels of
     // the merged BVH (breadth-first layout, so the first 256 nodes are its first ~3 levels: every ray visits several of them)
-    const bool flat_only = P.flat_root >= 0 && P.flat_all;
+    const bool flat_only = P.flat_root >= 0 && (P.flat_all || PTB_STAGE_MERGED_TOP);
     S.stage_base = flat_only ? unsigned(P.flat_root) : 0u;
     S.staged = flat_only ? min(P.flat_node_count, PTB_TLAS_STAGE_MAX_NODES) : min(P.tlas_nodes, PTB_TLAS_STAGE_MAX_NODES);
     S.tlas = tlas_sm;
@@ -1104,9 +1109,6 @@ PTB_DI float2 ellipse_axis_to_gradient(const TriFull& t, float inv_2area, float3
 // ------------------------------------------------------------------------------------------ shade + NEE + extend
 // Src/CUDA/Pathtracer.cu:465-757.  One kernel instantiation per BSDF; shadow rays and extension rays are appended
 // with warp-aggregated atomics.
-#ifndef PTB_SHADE_PREFETCH
-#define PTB_SHADE_PREFETCH 0
-#endif
 template <typename BSDF> struct ShadeOccupancy { static constexpr int min_blocks = 2; };        // microfacet BSDFs: ~120 registers
 template <> struct ShadeOccupancy<BSDFDiffuse> { static constexpr int min_blocks = PTB_SHADE_MIN_BLOCKS_DIFFUSE; };
 template <typename BSDF>
@@ -1119,11 +1121,6 @@ __global__ void __launch_bounds__(256, ShadeOccupancy<BSDF>::min_blocks) k_shade
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
         bool emit_shadow = false, emit_next = false;
         float4 sh0, sh1, sh_ill, nx0, nx1, nx_path; unsigned nx_pix = 0; int nx_medium = PTB_INVALID;
-#if PTB_SHADE_PREFETCH
-        const int i_next = i + int(gridDim.x * blockDim.x);
-        int index_next = -1;
-        if (i_next < count) index_next = __ldg(queue + i_next);     // issued now, consumed after this iteration's own loads are in flight
-#endif
         if (i < count) {
             const int index = queue[i];
             float4 a = q.od0[index], b = q.od1[index];
@@ -1141,13 +1138,6 @@ __global__ void __launch_bounds__(256, ShadeOccupancy<BSDF>::min_blocks) k_shade
             if (bounce > 0) { float4 p = q.path[index]; throughput = f3(p.x, p.y, p.z); }
 
             TriFull tri = load_tri_full(P, hit.triangle_id);
-#if PTB_SHADE_PREFETCH
-            if (index_next >= 0) {       // next iteration's gathered records -> L2 while this one computes
-                prefetch_l2(q.od0 + index_next); prefetch_l2(q.od1 + index_next); prefetch_l2(q.hit + index_next);
-                prefetch_l2(q.pix + index_next);
-                if (bounce > 0) prefetch_l2(q.path + index_next);
-            }
-#endif
             float3 hit_point = barycentric(hit.u, hit.v, tri.p0, tri.e1, tri.e2);
             float3 normal = barycentric(hit.u, hit.v, tri.n0, tri.ne1, tri.ne2);
             float2 tex_coord = barycentric(hit.u, hit.v, tri.t0, tri.te1, tri.te2);
