@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(PTB_TRACE_BLOCK, PTB_TRACE_MIN_BLOCKS) k_trace
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw);
     float4* tlas_sm = reinterpret_cast<float4*>(smem_raw + 16);
     TraceShared S;
-    // staged in shared memory: the TLAS, or -- when every instance is merged and the TLAS is never walked -- the top levels of
-    // the merged BVH (breadth-first layout, so the first 256 nodes are its first ~3 levels: every ray visits several of them)
+    // staged in shared memory: the top levels of the merged BVH when there is one (breadth-first layout, so its first 128 nodes are its
+    // first ~3 levels: every ray visits several of them), otherwise the TLAS
     const bool flat_only = P.flat_root >= 0 && (P.flat_all || PTB_STAGE_MERGED_TOP);
     S.stage_base = flat_only ? unsigned(P.flat_root) : 0u;
     S.staged = flat_only ? min(P.flat_node_count, PTB_TLAS_STAGE_MAX_NODES) : min(P.tlas_nodes, PTB_TLAS_STAGE_MAX_NODES);
