@@ -40,3 +40,16 @@ def test_reference_arm_is_rank0_only():
 def test_product_arm_refuses_to_run_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_committed_ncu_summaries_regenerate_from_the_raw_page(tmp_path):
+    """profiles/r2_all_kernels_ncu.csv and r2_trace8_ncu.csv (what bench.py reads roofline.traffic / issue_active / lanes_per_inst from)
+    are exactly what tools/ncu_summarize.py makes of the committed `ncu --page raw --csv` export of the final capture."""
+    import subprocess, sys
+    raw = os.path.join(ROOT, "profiles", "r2_final_ncu_raw_page.csv.gz")
+    if not os.path.exists(raw):
+        pytest.skip("raw page not committed")
+    out = str(tmp_path / "x")
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_summarize.py"), raw, out], stdout=subprocess.DEVNULL)
+    for suffix, committed in (("_all_kernels_ncu.csv", "r2_all_kernels_ncu.csv"), ("_trace8_ncu.csv", "r2_trace8_ncu.csv")):
+        assert open(out + suffix).read() == open(os.path.join(ROOT, "profiles", committed)).read(), committed
