@@ -166,6 +166,7 @@ extern "C" {
 void* ptbh_build_triangles(const float* pos, int n, int kind, float sah_node, float sah_leaf);
 void* ptbh_build_triangles_sbvh(const float* pos, int n, float alpha, int bins, float max_dup);
 void  ptbh_set_tri_cost(float c);
+void  ptbh_set_optimizer(int passes, float fraction, int max_depth);
 #ifndef PTB_MERGE_ALPHA_DEFAULT
 #define PTB_MERGE_ALPHA_DEFAULT 3e-4f
 #endif
@@ -174,6 +175,9 @@ void  ptbh_set_tri_cost(float c);
 #endif
 #ifndef PTB_MERGE_TRICOST_DEFAULT
 #define PTB_MERGE_TRICOST_DEFAULT 1.0f
+#endif
+#ifndef PTB_MERGE_OPTIMIZE_DEFAULT
+#define PTB_MERGE_OPTIMIZE_DEFAULT 1        // sweeps of the insertion-based optimiser over the merged tree's binary BVH (0 = off)
 #endif
 int   ptbh_node_count(void* h);
 int   ptbh_index_count(void* h);
@@ -740,9 +744,16 @@ static int rebuild_static_merge(ptb_ctx* ctx) {
         if (const char* v = getenv("PTB_MERGE_BINS")) bins = atoi(v);
         if (const char* v = getenv("PTB_MERGE_DUP")) dup = (float)atof(v);
         if (const char* v = getenv("PTB_MERGE_TRICOST")) tri_cost = (float)atof(v);
+        // insertion-based optimisation of the binary split BVH before the wide collapse (host/bvh_build.cpp ReinsertionOptimizer): on
+        // Sponza 8 % less SAH cost and 9-25 % fewer node visits per ray from four different views, closest hits unchanged, +2 s of build;
+        // the builder keeps the tree as built if the optimised one would not fit the traversal stack
+        int opt_passes = PTB_MERGE_OPTIMIZE_DEFAULT; float opt_fraction = 1.0f;
+        if (const char* v = getenv("PTB_MERGE_OPTIMIZE")) opt_passes = atoi(v);
+        if (const char* v = getenv("PTB_MERGE_OPT_FRACTION")) opt_fraction = (float)atof(v);
         ptbh_set_tri_cost(tri_cost);
+        ptbh_set_optimizer(opt_passes, opt_fraction, (PTB_STACK_TOTAL - 3) / 2);
         h = attempt == 0 ? ptbh_build_triangles_sbvh(pos.data(), n, alpha, bins, dup) : ptbh_build_triangles(pos.data(), n, 8, 4.0f, 1.0f);
-        ptbh_set_tri_cost(1.0f);
+        ptbh_set_tri_cost(1.0f); ptbh_set_optimizer(0, 1.0f, 0);
         if (!h) return PTB_E_STATE;
         nm = ptbh_node_count(h);
         dfs.assign((size_t)nm * 80, 0); order.assign((size_t)ptbh_index_count(h), 0);

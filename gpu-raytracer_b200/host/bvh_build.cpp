@@ -758,6 +758,96 @@ struct SpatialBuilder {
     }
 };
 
+// ---------------------------------------------------------------- insertion-based optimisation of a binary BVH
+// Bittner, Hapala, Havran 2013 ("Fast insertion-based optimization of bounding volume hierarchies"; the idea behind the reference's
+// Src/BVH/BVHOptimizer.cpp, own formulation): take a subtree out of the tree (its sibling moves up into the parent's slot), look for the
+// position where putting it back costs the least surface area -- branch and bound over the tree, cost of a position = area of the new
+// common parent + the growth of all its ancestors -- and link it in there with the freed pair of slots.  The original position is among
+// the candidates, so the tree's SAH cost never rises.  Works on the one-reference-per-leaf BVH2 of both builders (children in adjacent
+// slots (l, l + 1), l even, root 0, slot 1 unused); node boxes stay the exact union of their children.
+struct ReinsertionOptimizer {
+    std::vector<Node2>& nodes;
+    std::vector<int> parent;
+    explicit ReinsertionOptimizer(std::vector<Node2>& n) : nodes(n) {}
+
+    void link_children(int i) { if (!nodes[i].leaf()) { parent[nodes[i].left_or_first] = i; parent[nodes[i].left_or_first + 1] = i; } }
+    void refit_up(int i) {
+        while (i >= 0) {
+            Node2& n = nodes[i];
+            Box b = nodes[n.left_or_first].box; b.grow(nodes[n.left_or_first + 1].box);
+            n.box = b;
+            i = parent[i];
+        }
+    }
+    struct Item { float induced; int node; bool operator<(const Item& o) const { return induced > o.induced; } };   // min-heap on the induced cost
+
+    // best position for a detached subtree with box `nb`
+    int find_position(const Box& nb, std::vector<Item>& heap) {
+        const float na = nb.area();
+        float best = std::numeric_limits<float>::infinity(); int best_node = -1;
+        heap.clear(); heap.push_back({ 0.0f, 0 });
+        while (!heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end()); Item it = heap.back(); heap.pop_back();
+            if (it.induced + na >= best) break;                       // nothing cheaper left
+            const Node2& x = nodes[it.node];
+            Box u = x.box; u.grow(nb);
+            float direct = u.area(), total = it.induced + direct;
+            if (total < best) { best = total; best_node = it.node; }
+            float child_induced = total - x.box.area();
+            if (!x.leaf() && child_induced + na < best) {
+                heap.push_back({ child_induced, x.left_or_first }); std::push_heap(heap.begin(), heap.end());
+                heap.push_back({ child_induced, x.left_or_first + 1 }); std::push_heap(heap.begin(), heap.end());
+            }
+        }
+        return best_node;
+    }
+
+    // one reinsertion of the subtree in slot n; returns false when it cannot be moved (root, child of the root)
+    bool reinsert(int n, std::vector<Item>& heap) {
+        if (n < 2) return false;
+        const int p = parent[n];
+        if (p <= 0) return false;
+        const int s = n ^ 1, g = parent[p];
+        // detach: the sibling moves up into the parent's slot
+        nodes[p] = nodes[s]; link_children(p);
+        refit_up(g);
+        const Box nb = nodes[n].box;
+        int x = find_position(nb, heap);
+        if (x < 0) x = p;
+        // the freed pair (n, s) becomes the children of a new node in x's slot; x's old content moves to s
+        nodes[s] = nodes[x]; link_children(s);
+        Node2 np; np.box = nodes[s].box; np.box.grow(nb); np.left_or_first = n & ~1; np.set(0, 0);
+        nodes[x] = np;
+        parent[n] = x; parent[s] = x;
+        refit_up(parent[x]);
+        return true;
+    }
+
+    double sah() const {
+        double sum = 0.0;
+        for (size_t i = 0; i < nodes.size(); i++) if (i != 1) sum += double(nodes[i].box.area());
+        return sum / double(nodes[0].box.area());
+    }
+
+    // `passes` sweeps; every sweep offers the `fraction` largest nodes (by surface area) for reinsertion, largest first
+    void run(int passes, float fraction) {
+        const int total = int(nodes.size());
+        if (total < 8) return;
+        parent.assign(size_t(total), -1);
+        for (int i = 0; i < total; i++) if (i != 1) link_children(i);
+        std::vector<Item> heap; heap.reserve(1024);
+        std::vector<std::pair<float, int>> order; order.reserve(size_t(total));
+        for (int pass = 0; pass < passes; pass++) {
+            order.clear();
+            for (int i = 2; i < total; i++) order.push_back({ nodes[i].box.area(), i });
+            size_t take = size_t(double(order.size()) * double(fraction));
+            if (take < 1) take = 1; if (take > order.size()) take = order.size();
+            std::partial_sort(order.begin(), order.begin() + long(take), order.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first > b.first; });
+            for (size_t k = 0; k < take; k++) reinsert(order[k].second, heap);
+        }
+    }
+};
+
 struct Built {
     BVH2 bvh2;
     BVH4 bvh4;
@@ -854,6 +944,11 @@ void* ptbh_from_bvh2(const void* nodes, int n_nodes, const int* indices, int n_i
 // (e.g. 1.5).  ptbh_index_count() is the number of REFERENCES (>= n): indices may repeat a triangle.
 static float g_tri_cost = 1.0f;
 void ptbh_set_tri_cost(float c) { g_tri_cost = c; }     // tuning knob for tools/cpu_bvh_quality.py
+static int g_opt_passes = 0; static float g_opt_fraction = 1.0f; static int g_opt_max_depth = 0; static double g_opt_sah[2] = { 0.0, 0.0 };
+// insertion-based optimisation of the binary tree before the wide collapse (ReinsertionOptimizer): `passes` sweeps over the `fraction`
+// largest nodes; max_depth > 0 keeps the unoptimised tree when the optimised CWBVH would be deeper than that (traversal stack)
+void ptbh_set_optimizer(int passes, float fraction, int max_depth) { g_opt_passes = passes; g_opt_fraction = fraction; g_opt_max_depth = max_depth; }
+void ptbh_optimizer_sah(double* before_after) { before_after[0] = g_opt_sah[0]; before_after[1] = g_opt_sah[1]; }
 void* ptbh_build_triangles_sbvh(const float* pos, int n, float alpha, int bins, float max_dup) {
     if (n <= 0) return nullptr;
     SpatialBuilder sb; sb.pos = pos; sb.alpha = alpha; sb.bins = bins < 8 ? 8 : bins;
@@ -861,6 +956,16 @@ void* ptbh_build_triangles_sbvh(const float* pos, int n, float alpha, int bins, 
     sb.build(n);
     Built* b = new Built(); b->kind = 8;
     BVH2 raw; raw.nodes.swap(sb.nodes); raw.indices.swap(sb.indices);
+    if (g_opt_passes > 0) {
+        BVH2 opt = raw;
+        ReinsertionOptimizer ro(opt.nodes);
+        g_opt_sah[0] = ro.sah();
+        ro.run(g_opt_passes, g_opt_fraction);
+        g_opt_sah[1] = ro.sah();
+        WideConverter(opt, b->bvh8, g_tri_cost).run();
+        if (g_opt_max_depth <= 0 || ptb_merge::max_depth(reinterpret_cast<const unsigned char*>(b->bvh8.nodes.data()), 0) <= g_opt_max_depth) return b;
+        b->bvh8 = BVH8();                                   // too deep for the caller's stack: fall back to the tree as built
+    }
     WideConverter(raw, b->bvh8, g_tri_cost).run();
     return b;
 }

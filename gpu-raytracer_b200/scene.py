@@ -126,11 +126,27 @@ def build_blas_cached(mesh_file: str, tri, kind: int, sah_node=4.0, sah_leaf=1.0
     return blas_from_bvh2(nodes, indices, kind, sah_node, sah_leaf)
 
 
-def build_blas_sbvh(positions: np.ndarray, alpha=3e-4, bins=96, max_dup=2.0) -> BuiltBVH:
+def build_blas_sbvh(positions: np.ndarray, alpha=3e-4, bins=96, max_dup=2.0, optimize_passes=0, optimize_fraction=1.0, max_depth=0) -> BuiltBVH:
     """CWBVH over a split BVH (spatial splits; host/bvh_build.cpp SpatialBuilder).  index_count >= triangle count: a triangle may be
-    referenced by several leaves.  This is what libptb builds for the merged static BVH."""
+    referenced by several leaves.  This is what libptb builds for the merged static BVH.  optimize_passes > 0 runs the insertion-based
+    optimiser (ReinsertionOptimizer) over the binary tree before the wide collapse, like libptb does."""
     pos = np.ascontiguousarray(positions, dtype=f32).reshape(-1, 9)
-    return BuiltBVH(hostlib().ptbh_build_triangles_sbvh(pos.ctypes.data, pos.shape[0], alpha, bins, max_dup))
+    lib = hostlib()
+    lib.ptbh_set_optimizer.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_int]
+    lib.ptbh_set_optimizer(int(optimize_passes), float(optimize_fraction), int(max_depth))
+    try:
+        return BuiltBVH(lib.ptbh_build_triangles_sbvh(pos.ctypes.data, pos.shape[0], alpha, bins, max_dup))
+    finally:
+        lib.ptbh_set_optimizer(0, 1.0, 0)
+
+
+def optimizer_sah():
+    """(before, after): sum of node areas / root area of the binary tree of the last optimised build_blas_sbvh call."""
+    lib = hostlib()
+    v = (ctypes.c_double * 2)()
+    lib.ptbh_optimizer_sah.argtypes = [ctypes.c_void_p]
+    lib.ptbh_optimizer_sah(v)
+    return float(v[0]), float(v[1])
 
 
 def trace_stats(bvh: BuiltBVH, positions: np.ndarray, rays: np.ndarray):
