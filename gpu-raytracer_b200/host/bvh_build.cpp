@@ -942,9 +942,10 @@ void* ptbh_from_bvh2(const void* nodes, int n_nodes, const int* indices, int n_i
 // Split-BVH build (spatial splits) -> CWBVH.  alpha: minimum overlap of the object split's children, relative to the root's area,
 // for a spatial split to be tried (the reference's --sbvh-alpha, Config.h:58); max_dup: cap on references as a multiple of n
 // (e.g. 1.5).  ptbh_index_count() is the number of REFERENCES (>= n): indices may repeat a triangle.
-static float g_tri_cost = 1.0f;
+static thread_local float g_tri_cost = 1.0f;     // per calling thread: two contexts may build their merged trees concurrently
 void ptbh_set_tri_cost(float c) { g_tri_cost = c; }     // tuning knob for tools/cpu_bvh_quality.py
-static int g_opt_passes = 0; static float g_opt_fraction = 1.0f; static int g_opt_max_depth = 0; static double g_opt_sah[2] = { 0.0, 0.0 };
+static thread_local int g_opt_passes = 0; static thread_local float g_opt_fraction = 1.0f; static thread_local int g_opt_max_depth = 0;
+static thread_local double g_opt_sah[2] = { 0.0, 0.0 };
 // insertion-based optimisation of the binary tree before the wide collapse (ReinsertionOptimizer): `passes` sweeps over the `fraction`
 // largest nodes; max_depth > 0 keeps the unoptimised tree when the optimised CWBVH would be deeper than that (traversal stack)
 void ptbh_set_optimizer(int passes, float fraction, int max_depth) { g_opt_passes = passes; g_opt_fraction = fraction; g_opt_max_depth = max_depth; }
